@@ -1,0 +1,74 @@
+"""TEST INFRASTRUCTURE ONLY -- builds the *unmodified* reference CPU adam_op into oracle/_ref/.
+
+Compiles, where they lie under /root/reference (nothing is copied into this repo):
+    src/extension.cpp, src/adam_op/adam_op.cpp, src/adam_op/adam_op_impl_cpu.cpp
+with the reference's own flags (-O3 + OpenMP, no -march: CMakeLists.txt:37,48) into the CPython
+extension ``oracle/_ref/_C.so`` (``PYBIND11_MODULE(_C, mod)``, src/extension.cpp:20).  The result
+is (i) the primary parity oracle "O1", (ii) the generator of tests/golden/*.npz and (iii) the timed
+OpenMP CPU baseline of ``bench.py --impl reference``.  It is never imported by the product package.
+
+The reference's CMake build is NOT run (it hard-codes _GLIBCXX_USE_CXX11_ABI=0, which is wrong for the
+torch in this image); this is a 3-file g++ recipe.  ``/root/reference`` only exists in the build
+container; on the GPU box the prebuilt ``oracle/_ref/_C.so`` is used as is.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import sysconfig
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("TORCHOPT_REFERENCE", "/root/reference")
+OUT_DIR = os.path.join(HERE, "_ref")
+OUT = os.path.join(OUT_DIR, "_C.so")
+SOURCES = ["src/extension.cpp", "src/adam_op/adam_op.cpp", "src/adam_op/adam_op_impl_cpu.cpp"]
+
+
+def reference_present() -> bool:
+    return all(os.path.isfile(os.path.join(REF, s)) for s in SOURCES)
+
+
+def up_to_date() -> bool:
+    if not os.path.isfile(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    return all(os.path.getmtime(os.path.join(REF, s)) <= t for s in SOURCES)
+
+
+def build(force: bool = False, verbose: bool = True) -> str | None:
+    """Build oracle/_ref/_C.so; returns its path, or None when /root/reference is absent."""
+    if not reference_present():
+        return OUT if os.path.isfile(OUT) else None
+    if not force and up_to_date():
+        return OUT
+    import pybind11
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    os.makedirs(OUT_DIR, exist_ok=True)
+    torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    inc = [REF, pybind11.get_include(), sysconfig.get_paths()["include"], *ce.include_paths()]
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(OUT_DIR, src.replace("/", "_") + ".o")
+        cmd = ["g++", "-std=c++17", "-O3", "-fopenmp", "-fPIC", "-w",
+               f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+               "-DTORCH_API_INCLUDE_EXTENSION_H", "-DTORCH_EXTENSION_NAME=_C",
+               *[f"-I{p}" for p in inc], "-c", os.path.join(REF, src), "-o", obj]
+        if verbose:
+            print("[oracle/_ref]", " ".join(cmd[:6]), "...", src, flush=True)
+        subprocess.check_call(cmd)
+        objs.append(obj)
+    link = ["g++", "-shared", *objs, "-o", OUT, f"-L{torch_lib}", f"-Wl,-rpath,{torch_lib}",
+            "-ltorch_python", "-ltorch", "-ltorch_cpu", "-lc10",
+            "-L/usr/lib/gcc/x86_64-linux-gnu/13", "-lgomp"]
+    subprocess.check_call(link)
+    for o in objs:
+        os.remove(o)
+    return OUT
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv)
+    print(path if path else "reference sources not present and no prebuilt oracle/_ref/_C.so")
