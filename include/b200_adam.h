@@ -1,0 +1,164 @@
+/*
+ * b200_adam.h -- C ABI of libb200adam.so: the accelerated differentiable Adam operator for NVIDIA B200
+ * (sm_100a).  Plain pointers and sizes only; no torch / pybind types cross this boundary.
+ *
+ * This is the drop-in boundary for ONE path of metaopt/torchopt (v0.7.3): the native functions behind
+ * `torchopt._C.adam_op` (reference declarations: include/adam_op/adam_op.h:30-72, dispatcher
+ * src/adam_op/adam_op.cpp:32-153, CUDA launchers src/adam_op/adam_op_impl_cuda.cu:65-490).  Each entry
+ * point below names the reference launcher it replaces.  The reference-side binding a maintainer would
+ * add (the body of src/adam_op/adam_op.cpp calling these) is shown in INTEGRATION.md and shipped as
+ * torchopt_b200/csrc/torch_shim.cpp.
+ *
+ * Conventions
+ *  - Every array argument is a DEVICE pointer to `n` densely packed elements (element i of every argument
+ *    of one call is paired, exactly like the reference's data_ptr()[i] indexing, include/utils.h:27-34).
+ *  - `dtype` selects the element types:
+ *        B200_ADAM_F32       all arrays float            (arithmetic: IEEE fp32, no FMA contraction)
+ *        B200_ADAM_F64       all arrays double           (arithmetic: IEEE fp64, no FMA contraction)
+ *        B200_ADAM_BF16_F32  gradient-side arrays (updates / new_updates / dupdates in and out) are
+ *                            bfloat16, moment-side arrays (mu, nu, their grads) are float; arithmetic is
+ *                            fp32 on the up-cast inputs with ONE final rounding of bf16 outputs.
+ *                            Only the fused / in-place entry points accept it.
+ *  - Scalars arrive as the reference's pyfloat_t=double / pyuint_t=size_t (include/common.h:23-24).  The
+ *    bias corrections are derived on the host exactly as the reference does (std::pow in double, one
+ *    rounding to the tensor dtype: adam_op_impl_cuda.cu:73-75,253-255,452-454).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is enqueued
+ *    asynchronously on it; nothing synchronises.  The CUDA *current device* must own the pointers.
+ *  - Return value: 0 on success; a positive value is a cudaError_t; negative values are B200_ADAM_E_*.
+ *    n == 0 (or num_leaves == 0) is a successful no-op (the reference CPU path returns an empty tensor;
+ *    its CUDA path divides by zero on the host, adam_op_impl_cuda.cu:79-80).
+ *  - Results are bit-identical to the reference's CPU build (adam_op_impl_cpu.cpp) for F32 and F64,
+ *    including the mu'==0 branch, the fp64 tail of backward_updates, tails of any length and unaligned
+ *    pointers (which take a slower scalar path).
+ *  - Thread safety: all entry points are re-entrant; the library keeps no per-call state.
+ */
+#ifndef B200_ADAM_H_
+#define B200_ADAM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ADAM_ABI_VERSION 1
+
+enum b200_adam_dtype { B200_ADAM_F32 = 0, B200_ADAM_F64 = 1, B200_ADAM_BF16_F32 = 2 };
+
+enum b200_adam_error {
+  B200_ADAM_OK = 0,
+  B200_ADAM_E_DTYPE = -1,    /* dtype not supported by this entry point */
+  B200_ADAM_E_ARG = -2,      /* NULL pointer where an array is required, negative size, ... */
+  B200_ADAM_E_NO_DEVICE = -3 /* no CUDA device / not an sm_100 device */
+};
+
+/* ---- the seven operators of torchopt._C.adam_op (single tensor) -------------------------------- */
+
+/* forward_ : replaces adamForwardInplaceCUDA (adam_op_impl_cuda.cu:65-112).  In place: updates <- u,
+ * mu <- mu', nu <- nu'.  The three pointers may alias each other (is_available() passes one tensor three
+ * times, accelerated_op/__init__.py:46-47); per element all reads precede the writes mu, nu, updates. */
+int b200_adam_forward_inplace(int dtype, void *updates, void *mu, void *nu, int64_t n, double b1, double b2,
+                              double eps, double eps_root, uint64_t count, void *stream);
+
+/* forward_mu : replaces adamForwardMuCUDA (adam_op_impl_cuda.cu:135-165).  mu_out = b1*mu + (1-b1)*updates */
+int b200_adam_forward_mu(int dtype, const void *updates, const void *mu, void *mu_out, int64_t n, double b1,
+                         void *stream);
+
+/* forward_nu : replaces adamForwardNuCUDA (:189-219).  nu_out = b2*nu + ((1-b2)*updates)*updates */
+int b200_adam_forward_nu(int dtype, const void *updates, const void *nu, void *nu_out, int64_t n, double b2,
+                         void *stream);
+
+/* forward_updates : replaces adamForwardUpdatesCUDA (:246-291).
+ * updates_out = (new_mu*c1) / (sqrt(new_nu*c2 + eps_root) + eps) */
+int b200_adam_forward_updates(int dtype, const void *new_mu, const void *new_nu, void *updates_out, int64_t n,
+                              double b1, double b2, double eps, double eps_root, uint64_t count, void *stream);
+
+/* backward_mu : replaces adamBackwardMuCUDA (:314-346).  dupdates_out = (1-b1)*dmu ; dmu_out = b1*dmu */
+int b200_adam_backward_mu(int dtype, const void *dmu, void *dupdates_out, void *dmu_out, int64_t n, double b1,
+                          void *stream);
+
+/* backward_nu : replaces adamBackwardNuCUDA (:371-405).
+ * dupdates_out = ((2*(1-b2))*updates)*dnu ; dnu_out = b2*dnu */
+int b200_adam_backward_nu(int dtype, const void *dnu, const void *updates, void *dupdates_out, void *dnu_out,
+                          int64_t n, double b2, void *stream);
+
+/* backward_updates : replaces adamBackwardUpdatesCUDA (:444-490); CPU semantics (adam_op_impl_cpu.cpp:298-316):
+ * every element is processed (`continue`, not `return`, on new_mu == 0) and no tail is dropped. */
+int b200_adam_backward_updates(int dtype, const void *dupdates, const void *updates, const void *new_mu,
+                               void *dnew_mu_out, void *dnew_nu_out, int64_t n, double b1, double b2,
+                               double eps_root, uint64_t count, void *stream);
+
+/* ---- fused, multi-tensor entry points (new; one launch covers all pytree leaves) ----------------- */
+
+/* Differentiable forward of one Adam step for `num_leaves` leaves in ONE launch (24 B/element fp32):
+ *   mu_out = forward_mu(g, mu) ; nu_out = forward_nu(g, nu) ; u_out = forward_updates(mu_out, nu_out, count)
+ * i.e. what AdamOp.__call__(inplace=False) computes with three launches per leaf
+ * (accelerated_op/adam_op.py:168-180).  Arrays of `num_leaves` device pointers / sizes / counts live in
+ * HOST memory and are consumed before the call returns.  Outputs must not alias inputs (use
+ * b200_adam_forward_inplace_mt for that).  Leaves with n[i] == 0 are skipped. */
+int b200_adam_fused_forward(int dtype, int64_t num_leaves, const void *const *g, const void *const *mu,
+                            const void *const *nu, void *const *mu_out, void *const *nu_out, void *const *u_out,
+                            const int64_t *n, const uint64_t *count, double b1, double b2, double eps,
+                            double eps_root, void *stream);
+
+/* Multi-tensor forward_ (in place over g/mu/nu of every leaf; aliasing allowed as in forward_). */
+int b200_adam_forward_inplace_mt(int dtype, int64_t num_leaves, void *const *updates, void *const *mu,
+                                 void *const *nu, const int64_t *n, const uint64_t *count, double b1, double b2,
+                                 double eps, double eps_root, void *stream);
+
+/* Differentiable backward of one Adam step for `num_leaves` leaves in ONE launch (36 B/element fp32).
+ * Equals UpdatesOp.backward -> engine accumulation with the incoming moment gradients -> MuOp.backward and
+ * NuOp.backward -> engine accumulation of the two dupdates (accelerated_op/adam_op.py:105-121,53-60,79-86):
+ *   (dmu', dnu')   = backward_updates(du, u, new_mu, count)          [skipped when du[i] == NULL]
+ *   dmu_tot        = dmu_ext + dmu'   (either may be absent)         dnu_tot likewise
+ *   (dg_mu, dmu)   = backward_mu(dmu_tot)                            [absent when dmu_tot is absent]
+ *   (dg_nu, dnu)   = backward_nu(dnu_tot, g)
+ *   dg             = dg_mu + dg_nu    (0 when both absent)
+ * Per leaf, du[i], dmu_ext[i], dnu_ext[i] may be NULL (= no gradient flows in), and dg[i], dmu[i], dnu[i] may
+ * be NULL (= that output is not needed and is not written).  When an output is requested but its value is
+ * "absent" (no contributing gradient) zeros are written.  u, new_mu are required when du[i] != NULL; g is
+ * required when dnu_tot exists and dg[i] != NULL. */
+int b200_adam_fused_backward(int dtype, int64_t num_leaves, const void *const *du, const void *const *u,
+                             const void *const *new_mu, const void *const *g, const void *const *dmu_ext,
+                             const void *const *dnu_ext, void *const *dg, void *const *dmu, void *const *dnu,
+                             const int64_t *n, const uint64_t *count, double b1, double b2, double eps_root,
+                             void *stream);
+
+/* ---- host-buffer entry point (what an application holding HOST arrays calls; used for the e2e number) */
+
+/* One fused differentiable forward + backward over HOST arrays of n elements (dtype F32 only):
+ * inputs g, mu, nu, du, dmu_ext, dnu_ext; outputs mu_out, nu_out, u_out, dg, dmu, dnu (all host pointers,
+ * ideally page-locked).  The range is cut into slices that are copied in, processed by the two fused kernels
+ * and copied out on three streams so H2D, compute and D2H overlap.  Blocks until the outputs are complete.
+ * `slice_elems` <= 0 selects the default slice. */
+int b200_adam_host_step_f32(const float *g, const float *mu, const float *nu, const float *du,
+                            const float *dmu_ext, const float *dnu_ext, float *mu_out, float *nu_out,
+                            float *u_out, float *dg, float *dmu, float *dnu, int64_t n, double b1, double b2,
+                            double eps, double eps_root, uint64_t count, int64_t slice_elems);
+
+/* Frees the device staging buffers / streams cached by b200_adam_host_step_f32 (optional). */
+int b200_adam_host_release(void);
+
+/* ---- utilities ------------------------------------------------------------------------------------ */
+
+int b200_adam_abi_version(void);
+
+/* Human-readable text for a return code of this library (never NULL). */
+const char *b200_adam_error_string(int code);
+
+/* Number of CUDA kernels this library has launched in this process so far (for bench.py's gpu_launches). */
+uint64_t b200_adam_kernel_launches(void);
+
+/* Launch tuning: resident CTAs per SM of the persistent grid (0 = library default) and the number of
+ * block-tiles per chunk (0 = default).  Process-wide; intended for the bench/tuning harness. */
+int b200_adam_set_tuning(int ctas_per_sm, int tiles_per_chunk);
+
+/* Writes the launch geometry the library would use for an `n`-element single-leaf fused launch:
+ * out[0]=grid, out[1]=block, out[2]=elements per chunk, out[3]=vector width in elements, out[4]=unroll. */
+int b200_adam_query_launch(int dtype, int backward, int64_t n, int32_t out[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_ADAM_H_ */

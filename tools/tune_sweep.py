@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""On-device sweep of the streaming-engine launch parameters for the fp32 fused kernels.
+
+    python tools/tune_sweep.py --build     # CPU box: compile the variant libraries into build/tune/
+    python tools/tune_sweep.py --run       # GPU box: time every variant, write gpurun_out/tune_sweep.json
+
+A variant = (vector width P, unroll U, CTA size) baked in at compile time (-DB200_P_FWD=.. etc.) x run-time
+(ctas_per_sm, tiles_per_chunk) set through b200_adam_set_tuning.  Timing: CUDA events, 3 warm-ups + 10 launches,
+n = 2^28 elements per array (arrays >> L2).  The winner is recorded in profiles/ and hard-wired as the default in
+torchopt_b200/csrc/b200_adam.cu.
+"""
+from __future__ import annotations
+
+import argparse
+import itertools
+import json
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT_DIR = os.path.join(ROOT, "build", "tune")
+VARIANTS = [(p, u, b) for p, u in ((4, 1), (4, 2), (4, 4), (8, 1), (8, 2), (8, 4)) for b in (128, 256, 512)]
+
+
+def lib_path(p, u, b):
+    return os.path.join(OUT_DIR, f"libb200adam_P{p}U{u}B{b}.so")
+
+
+def build_one(v):
+    p, u, b = v
+    csrc = os.path.join(ROOT, "torchopt_b200", "csrc")
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--fmad=false",
+           "-Xcompiler", "-fPIC", "-shared", "-DB200_ADAM_TUNE_F32_ONLY", f"-DB200_ADAM_BLOCK={b}",
+           f"-DB200_P_FWD={p}", f"-DB200_U_FWD={u}", f"-DB200_P_BWD={p}", f"-DB200_U_BWD={u}",
+           f"-I{os.path.join(ROOT, 'include')}", f"-I{csrc}", os.path.join(csrc, "b200_adam.cu"),
+           os.path.join(csrc, "host_pipeline.cu"), "-o", lib_path(p, u, b)]
+    subprocess.check_call(cmd)
+    return v
+
+
+def build():
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        for v in ex.map(build_one, VARIANTS):
+            print("built", v, flush=True)
+
+
+def run(n_log2: int, out_path: str):
+    import torch
+    from torchopt_b200 import abi
+
+    n = 1 << n_log2
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    t = [torch.randn(n, device=dev) * s for s in (1e-2, 1e-2, 1.0, 1.0, 1e-3, 1e-3)]
+    t[2] = t[2].abs() * 1e-4
+    o = [torch.empty(n, device=dev) for _ in range(6)]
+    g, mu, nu, du, dme, dne = (x.data_ptr() for x in t)
+    mu2, nu2, u, dg, dmu, dnu = (x.data_ptr() for x in o)
+    stream = torch.cuda.current_stream().cuda_stream
+    results = []
+    for (p, uu, b) in VARIANTS:
+        path = lib_path(p, uu, b)
+        if not os.path.isfile(path):
+            continue
+        lib = abi.load(path)
+        prep = abi.PreparedFused.__new__(abi.PreparedFused)
+        prep.lib, prep.dtype, prep.L = lib, abi.F32, 1
+        prep.n, prep.count = abi._arr(abi.c_int64, [n]), abi._arr(abi.c_uint64, [3])
+        prep.fwd = [abi._ptrs([x]) for x in (g, mu, nu, mu2, nu2, u)]
+        prep.bwd = [abi._ptrs([x]) for x in (du, u, mu2, g, dme, dne, dg, dmu, dnu)]
+        prep.h = (0.9, 0.999, 1e-8, 1e-8)
+        for ctas, tiles in itertools.product((0, 1, 2, 4, 8, 16, 1 << 20), (1, 2, 4, 8)):
+            assert lib.b200_adam_set_tuning(ctas, tiles) == 0
+            row = {"P": p, "U": uu, "block": b, "ctas_per_sm": ctas, "tiles_per_chunk": tiles}
+            for name, fn, nbytes in (("fwd", prep.forward, 24 * n), ("bwd", prep.backward, 36 * n)):
+                for _ in range(3):
+                    assert fn(stream) == 0
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    fn(stream)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 10
+                row[f"{name}_ms"] = ms
+                row[f"{name}_gbs"] = nbytes / (ms * 1e-3) / 1e9
+            results.append(row)
+            print(json.dumps(row), flush=True)
+    # reference points: torch copy_ (the MEASURED_PEAKS method) on the same arrays
+    for _ in range(3):
+        o[0].copy_(t[0])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        o[0].copy_(t[0])
+    e1.record()
+    torch.cuda.synchronize()
+    copy_gbs = 8 * n / (e0.elapsed_time(e1) / 10 * 1e-3) / 1e9
+    best_f = max(results, key=lambda r: r["fwd_gbs"])
+    best_b = max(results, key=lambda r: r["bwd_gbs"])
+    summary = {"n": n, "torch_copy_gbs": copy_gbs, "best_fwd": best_f, "best_bwd": best_b, "rows": results}
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    with open(out_path, "w") as f:
+        json.dump(summary, f, indent=1)
+    print("torch copy_ GB/s", copy_gbs)
+    print("BEST fwd", json.dumps(best_f))
+    print("BEST bwd", json.dumps(best_b))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--build", action="store_true")
+    ap.add_argument("--run", action="store_true")
+    ap.add_argument("--n-log2", type=int, default=28)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "tune_sweep.json"))
+    a = ap.parse_args()
+    if a.build:
+        build()
+    if a.run:
+        run(a.n_log2, a.out)

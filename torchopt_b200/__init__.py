@@ -1,0 +1,27 @@
+"""torchopt_b200 -- the accelerated differentiable Adam operator of metaopt/torchopt, rebuilt for NVIDIA B200.
+
+One hot path only: ``torchopt._C.adam_op`` + ``torchopt.accelerated_op.AdamOp``, as
+hand-written sm_100a CUDA kernels behind a C ABI (include/b200_adam.h).  Importing this package loads the native
+extension and fails loudly if it has not been built -- there is no CPU or pure-Python fallback.
+
+    torchopt_b200._C.adam_op            the reference's seven operators (+ fused multi-tensor entry points)
+    torchopt_b200.accelerated_op        AdamOp, is_available
+    torchopt_b200.transform             scale_by_accelerated_adam, ScaleByAdamState
+    torchopt_b200.optim                 adam, apply_updates, MetaAdam, Adam   (thin callers)
+    torchopt_b200.abi                   ctypes binding of the raw C ABI
+    torchopt_b200.parallel              flat-shard partitioning, task-parallel meta-gradient all-reduce
+"""
+from torchopt_b200._native import _C, adam_op
+from torchopt_b200 import abi, accelerated_op, optim, parallel, transform
+from torchopt_b200.accelerated_op import AdamOp
+from torchopt_b200.accelerated_op import is_available as accelerated_op_available
+from torchopt_b200.optim import Adam, MetaAdam, adam, apply_updates
+from torchopt_b200.transform import GradientTransformation, ScaleByAdamState, scale_by_accelerated_adam
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "_C", "adam_op", "abi", "accelerated_op", "optim", "parallel", "transform",
+    "AdamOp", "accelerated_op_available", "Adam", "MetaAdam", "adam", "apply_updates",
+    "GradientTransformation", "ScaleByAdamState", "scale_by_accelerated_adam",
+]

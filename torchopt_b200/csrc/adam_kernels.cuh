@@ -1,0 +1,541 @@
+// adam_kernels.cuh -- device code of the B200 (sm_100a) accelerated differentiable Adam operator.
+//
+// One streaming engine (`stream_kernel`) + one small policy struct per operator.  Every operator of the
+// path is an element-wise HBM stream (arithmetic intensity < 1 flop/B, no contraction => no tensor cores),
+// so the engine is built for bytes in flight:
+//   * 128-bit or 256-bit (LDG.E.256 / STG.E.256, new on sm_100) vector accesses, fully coalesced: lane k of a
+//     warp touches vector k of a 32-vector run; the read-only streams use ld.global.nc + L1::no_allocate;
+//   * U independent vector loads per array are issued front-batched before any use (MLP = U x arrays);
+//   * persistent CTAs walk "chunks" (a chunk = a few block-tiles of ONE leaf) in grid-stride order, so the
+//     CTAs resident at any instant cover one contiguous window of every array;
+//   * multi-tensor: the leaf table (pointers, sizes, per-leaf bias corrections, chunk prefix sums) rides in
+//     the kernel parameters (__grid_constant__, up to 32 KB on sm_100) -- no device-side table, no extra copy,
+//     graph-capturable; a single flat tensor is simply the 1-leaf table.
+//
+// Arithmetic contract (reference loops in /root/reference/src/adam_op/adam_op_impl_cpu.cpp):
+// every * + / sqrt is one correctly rounded IEEE operation in the tensor dtype, in the reference's source order,
+// never contracted into FMA (explicit __f*_rn / __d*_rn intrinsics), subnormals kept.  Results are therefore
+// bit-identical to the reference CPU build.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200adam {
+
+// ------------------------------------------------------------------------------------------------
+// element types
+// ------------------------------------------------------------------------------------------------
+struct bf16_t {
+  uint16_t bits;
+};
+
+template <typename CT>
+struct Math;
+
+template <>
+struct Math<float> {
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+  // tail of backward_updates: the reference's literal 0.5 is a double, so (t*0.5*c2e*den) is evaluated in
+  // fp64 and rounded to float once (adam_op_impl_cpu.cpp:315-316).
+  static __device__ __forceinline__ float dnu_tail(float t, float c2e, float den) {
+    const double x = __dmul_rn(__dmul_rn(__dmul_rn((double)t, 0.5), (double)c2e), (double)den);
+    return __double2float_rn(x);
+  }
+};
+
+template <>
+struct Math<double> {
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+  static __device__ __forceinline__ double dnu_tail(double t, double c2e, double den) {
+    return __dmul_rn(__dmul_rn(__dmul_rn(t, 0.5), c2e), den);
+  }
+};
+
+template <typename CT, typename T>
+__device__ __forceinline__ CT up(T v) {
+  return (CT)v;
+}
+template <>
+__device__ __forceinline__ float up<float, bf16_t>(bf16_t v) {
+  return __uint_as_float(((uint32_t)v.bits) << 16);  // exact
+}
+
+template <typename T, typename CT>
+struct Down {
+  static __device__ __forceinline__ T cvt(CT v) { return (T)v; }
+};
+template <>
+struct Down<bf16_t, float> {
+  // round-to-nearest-even float -> bf16, NaN kept quiet (same result as __float2bfloat16_rn)
+  static __device__ __forceinline__ bf16_t cvt(float f) {
+    uint32_t x = __float_as_uint(f);
+    bf16_t r;
+    if ((x & 0x7fffffffu) > 0x7f800000u) {
+      r.bits = 0x7fffu;
+    } else {
+      x += 0x7fffu + ((x >> 16) & 1u);
+      r.bits = (uint16_t)(x >> 16);
+    }
+    return r;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// vector global-memory access: BYTES in {8, 16, 32}; NC = read-only (non-coherent) path allowed
+// ------------------------------------------------------------------------------------------------
+template <int BYTES, bool NC>
+struct VecIO;
+
+template <bool NC>
+struct VecIO<32, NC> {
+  static __device__ __forceinline__ void ld(uint32_t (&w)[8], const void *p) {
+    if (NC)
+      asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                   : "l"(p));
+    else
+      asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                   : "l"(p)
+                   : "memory");
+  }
+  static __device__ __forceinline__ void st(void *p, const uint32_t (&w)[8]) {
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]),
+                 "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+  }
+};
+
+template <bool NC>
+struct VecIO<16, NC> {
+  static __device__ __forceinline__ void ld(uint32_t (&w)[4], const void *p) {
+    if (NC)
+      asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                   : "l"(p));
+    else
+      asm volatile("ld.global.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                   : "l"(p)
+                   : "memory");
+  }
+  static __device__ __forceinline__ void st(void *p, const uint32_t (&w)[4]) {
+    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(w[0]), "r"(w[1]),
+                 "r"(w[2]), "r"(w[3])
+                 : "memory");
+  }
+};
+
+template <bool NC>
+struct VecIO<8, NC> {
+  static __device__ __forceinline__ void ld(uint32_t (&w)[2], const void *p) {
+    if (NC)
+      asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p));
+    else
+      asm volatile("ld.global.L1::no_allocate.v2.b32 {%0,%1}, [%2];"
+                   : "=r"(w[0]), "=r"(w[1])
+                   : "l"(p)
+                   : "memory");
+  }
+  static __device__ __forceinline__ void st(void *p, const uint32_t (&w)[2]) {
+    asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(w[0]), "r"(w[1]) : "memory");
+  }
+};
+
+// P elements of type T held in registers; loaded/stored as ONE vector access when P > 1.
+template <typename T, int P>
+union Pack {
+  T v[P];
+  uint32_t w[(sizeof(T) * P + 3) / 4];
+  __device__ __forceinline__ Pack() {}
+};
+
+template <bool NC, typename T, int P>
+__device__ __forceinline__ void load_pack(Pack<T, P> &r, const T *p) {
+  if constexpr (P == 1) {
+    r.v[0] = *p;
+  } else {
+    VecIO<(int)sizeof(T) * P, NC>::ld(r.w, p);
+  }
+}
+
+template <typename T, int P>
+__device__ __forceinline__ void store_pack(T *p, const Pack<T, P> &r) {
+  if constexpr (P == 1) {
+    *p = r.v[0];
+  } else {
+    VecIO<(int)sizeof(T) * P, false>::st(p, r.w);
+  }
+}
+
+template <typename T, int P>
+__device__ __forceinline__ bool is_aligned(const void *p) {
+  return (reinterpret_cast<uintptr_t>(p) & (uintptr_t)(sizeof(T) * P - 1)) == 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// leaf table (kernel parameter)
+// ------------------------------------------------------------------------------------------------
+template <class Op, int MAXL>
+struct Table {
+  int num_leaves;
+  int chunk_elems;   // elements per chunk; a multiple of the block tile (hence of the vector width)
+  int total_chunks;  // == chunk_start[num_leaves]
+  int flags;         // operator specific
+  typename Op::CT gs[Op::NGS];  // scalars shared by all leaves (betas, eps, ...)
+  int chunk_start[MAXL + 1];    // exclusive prefix sum of per-leaf chunk counts
+  long long n[MAXL];
+  void *ptr[Op::NPTR][MAXL];
+  typename Op::CT ls[Op::NLS > 0 ? Op::NLS : 1][MAXL];  // per-leaf scalars (bias corrections: depend on count)
+};
+
+// ------------------------------------------------------------------------------------------------
+// operators
+// ------------------------------------------------------------------------------------------------
+// forward of one differentiable Adam step: reads g, mu, nu ; writes mu', nu', u.
+//   mu' = (B1*mu) + (OMB1*g)                    adam_op_impl_cpu.cpp:105
+//   nu' = (B2*nu) + ((OMB2*g)*g)                adam_op_impl_cpu.cpp:140
+//   u   = (mu'*C1) / (sqrt((nu'*C2)+ER) + EPS)  adam_op_impl_cpu.cpp:176-179
+// INPLACE = outputs may alias inputs (forward_, adam_op_impl_cpu.cpp:46-60): coherent loads, and the stores
+// are issued in the reference's order mu, nu, updates so that fully aliased arguments end up holding u.
+template <typename TG_, typename TS_, typename CT_, bool INPLACE>
+struct FusedFwd {
+  using TG = TG_;
+  using TS = TS_;
+  using CT = CT_;
+  static constexpr int NPTR = 6, NGS = 6, NLS = 2;
+  struct Leaf {
+    const TG *g;
+    const TS *mu, *nu;
+    TS *mu_o, *nu_o;
+    TG *u_o;
+    CT B1, OMB1, B2, OMB2, ER, EPS, C1, C2;
+  };
+  template <class Tab>
+  static __device__ __forceinline__ Leaf leaf(const Tab &t, int l) {
+    Leaf L;
+    L.g = (const TG *)t.ptr[0][l];
+    L.mu = (const TS *)t.ptr[1][l];
+    L.nu = (const TS *)t.ptr[2][l];
+    L.mu_o = (TS *)t.ptr[3][l];
+    L.nu_o = (TS *)t.ptr[4][l];
+    L.u_o = (TG *)t.ptr[5][l];
+    L.B1 = t.gs[0], L.OMB1 = t.gs[1], L.B2 = t.gs[2], L.OMB2 = t.gs[3], L.ER = t.gs[4], L.EPS = t.gs[5];
+    L.C1 = t.ls[0][l], L.C2 = t.ls[1][l];
+    return L;
+  }
+  template <int P>
+  static __device__ __forceinline__ bool aligned(const Leaf &L) {
+    return is_aligned<TG, P>(L.g) && is_aligned<TS, P>(L.mu) && is_aligned<TS, P>(L.nu) &&
+           is_aligned<TS, P>(L.mu_o) && is_aligned<TS, P>(L.nu_o) && is_aligned<TG, P>(L.u_o);
+  }
+  template <int P>
+  struct Regs {
+    Pack<TG, P> g;  // becomes u
+    Pack<TS, P> mu, nu;
+  };
+  template <int P>
+  static __device__ __forceinline__ void load(Regs<P> &r, const Leaf &L, long long i) {
+    load_pack<!INPLACE>(r.g, L.g + i);
+    load_pack<!INPLACE>(r.mu, L.mu + i);
+    load_pack<!INPLACE>(r.nu, L.nu + i);
+  }
+  template <int P>
+  static __device__ __forceinline__ void compute(Regs<P> &r, const Leaf &L) {
+    using M = Math<CT>;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const CT g = up<CT>(r.g.v[k]), m = up<CT>(r.mu.v[k]), v = up<CT>(r.nu.v[k]);
+      const CT m_out = M::add(M::mul(L.B1, m), M::mul(L.OMB1, g));
+      const CT v_out = M::add(M::mul(L.B2, v), M::mul(M::mul(L.OMB2, g), g));
+      const CT m_hat = M::mul(m_out, L.C1);
+      const CT v_hat = M::mul(v_out, L.C2);
+      const CT u = M::div(m_hat, M::add(M::sqrt(M::add(v_hat, L.ER)), L.EPS));
+      r.mu.v[k] = Down<TS, CT>::cvt(m_out);
+      r.nu.v[k] = Down<TS, CT>::cvt(v_out);
+      r.g.v[k] = Down<TG, CT>::cvt(u);
+    }
+  }
+  template <int P>
+  static __device__ __forceinline__ void store(const Regs<P> &r, const Leaf &L, long long i) {
+    store_pack(L.mu_o + i, r.mu);
+    store_pack(L.nu_o + i, r.nu);
+    store_pack(L.u_o + i, r.g);
+  }
+};
+
+// backward of one differentiable Adam step (see include/b200_adam.h, b200_adam_fused_backward).
+// MODE: 0 = every leaf has du, dmu_ext, dnu_ext and wants dg, dmu, dnu (general unroll step, 36 B/elem)
+//       1 = every leaf has du only and wants dg, dmu, dnu         (last unroll step, 28 B/elem)
+//       2 = per-leaf presence decided at run time from NULL pointers (uniform per chunk)
+enum { BWD_FULL = 0, BWD_LAST = 1, BWD_GENERIC = 2 };
+
+template <typename TG_, typename TS_, typename CT_, int MODE>
+struct FusedBwd {
+  using TG = TG_;
+  using TS = TS_;
+  using CT = CT_;
+  static constexpr int NPTR = 9, NGS = 4, NLS = 2;
+  struct Leaf {
+    const TG *du, *u, *g;
+    const TS *m, *dmu_ext, *dnu_ext;
+    TG *dg;
+    TS *dmu, *dnu;
+    CT B1, OMB1, B2, TWO_OMB2, O1, C2E;
+  };
+  template <class Tab>
+  static __device__ __forceinline__ Leaf leaf(const Tab &t, int l) {
+    Leaf L;
+    L.du = (const TG *)t.ptr[0][l];
+    L.u = (const TG *)t.ptr[1][l];
+    L.m = (const TS *)t.ptr[2][l];
+    L.g = (const TG *)t.ptr[3][l];
+    L.dmu_ext = (const TS *)t.ptr[4][l];
+    L.dnu_ext = (const TS *)t.ptr[5][l];
+    L.dg = (TG *)t.ptr[6][l];
+    L.dmu = (TS *)t.ptr[7][l];
+    L.dnu = (TS *)t.ptr[8][l];
+    L.B1 = t.gs[0], L.OMB1 = t.gs[1], L.B2 = t.gs[2], L.TWO_OMB2 = t.gs[3];
+    L.O1 = t.ls[0][l], L.C2E = t.ls[1][l];
+    return L;
+  }
+  static __device__ __forceinline__ bool has_du(const Leaf &L) { return MODE != BWD_GENERIC || L.du != nullptr; }
+  static __device__ __forceinline__ bool has_dmu_ext(const Leaf &L) {
+    return MODE == BWD_FULL || (MODE == BWD_GENERIC && L.dmu_ext != nullptr);
+  }
+  static __device__ __forceinline__ bool has_dnu_ext(const Leaf &L) {
+    return MODE == BWD_FULL || (MODE == BWD_GENERIC && L.dnu_ext != nullptr);
+  }
+  static __device__ __forceinline__ bool want_dg(const Leaf &L) { return MODE != BWD_GENERIC || L.dg != nullptr; }
+  static __device__ __forceinline__ bool want_dmu(const Leaf &L) { return MODE != BWD_GENERIC || L.dmu != nullptr; }
+  static __device__ __forceinline__ bool want_dnu(const Leaf &L) { return MODE != BWD_GENERIC || L.dnu != nullptr; }
+  // g is read only if a dnu_tot exists and dg is wanted
+  static __device__ __forceinline__ bool need_g(const Leaf &L) {
+    return want_dg(L) && (has_du(L) || has_dnu_ext(L));
+  }
+
+  template <int P>
+  static __device__ __forceinline__ bool aligned(const Leaf &L) {
+    // NULL pointers are aligned by construction
+    return is_aligned<TG, P>(L.du) && is_aligned<TG, P>(L.u) && is_aligned<TS, P>(L.m) &&
+           is_aligned<TG, P>(L.g) && is_aligned<TS, P>(L.dmu_ext) && is_aligned<TS, P>(L.dnu_ext) &&
+           is_aligned<TG, P>(L.dg) && is_aligned<TS, P>(L.dmu) && is_aligned<TS, P>(L.dnu);
+  }
+  template <int P>
+  struct Regs {
+    Pack<TG, P> du, u, g;      // g becomes dg
+    Pack<TS, P> m, dme, dne;   // dme/dne become dmu/dnu
+  };
+  template <int P>
+  static __device__ __forceinline__ void load(Regs<P> &r, const Leaf &L, long long i) {
+    if (has_du(L)) {
+      load_pack<true>(r.du, L.du + i);
+      load_pack<true>(r.u, L.u + i);
+      load_pack<true>(r.m, L.m + i);
+    }
+    if (need_g(L)) load_pack<true>(r.g, L.g + i);
+    if (has_dmu_ext(L)) load_pack<true>(r.dme, L.dmu_ext + i);
+    if (has_dnu_ext(L)) load_pack<true>(r.dne, L.dnu_ext + i);
+  }
+  template <int P>
+  static __device__ __forceinline__ void compute(Regs<P> &r, const Leaf &L) {
+    using M = Math<CT>;
+    const bool hdu = has_du(L), hme = has_dmu_ext(L), hne = has_dnu_ext(L), ng = need_g(L);
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      CT dmu_tot = CT(0), dnu_tot = CT(0);
+      if (hdu) {
+        // backward_updates, adam_op_impl_cpu.cpp:298-316
+        const CT du = up<CT>(r.du.v[k]), u = up<CT>(r.u.v[k]), m = up<CT>(r.m.v[k]);
+        CT dm_new = CT(0), dn_new = CT(0);
+        if (m != CT(0)) {
+          const CT q = M::div(u, m);
+          const CT den = M::mul(q, L.O1);
+          dm_new = M::mul(du, q);
+          const CT t = M::mul(M::mul(-du, u), den);
+          dn_new = M::dnu_tail(t, L.C2E, den);
+        }
+        // autograd-engine accumulation with the gradients arriving from later steps (two addends: exact order-free)
+        dmu_tot = hme ? M::add(up<CT>(r.dme.v[k]), dm_new) : dm_new;
+        dnu_tot = hne ? M::add(up<CT>(r.dne.v[k]), dn_new) : dn_new;
+      } else {
+        if (hme) dmu_tot = up<CT>(r.dme.v[k]);
+        if (hne) dnu_tot = up<CT>(r.dne.v[k]);
+      }
+      const bool have_m = hdu || hme, have_n = hdu || hne;
+      // backward_mu, adam_op_impl_cpu.cpp:223-224 ; backward_nu, :261-262
+      const CT dg_mu = M::mul(L.OMB1, dmu_tot);
+      const CT dg_nu = ng ? M::mul(M::mul(L.TWO_OMB2, up<CT>(r.g.v[k])), dnu_tot) : CT(0);
+      const CT dg = (have_m && have_n) ? M::add(dg_mu, dg_nu) : (have_m ? dg_mu : dg_nu);
+      r.dme.v[k] = Down<TS, CT>::cvt(have_m ? M::mul(L.B1, dmu_tot) : CT(0));
+      r.dne.v[k] = Down<TS, CT>::cvt(have_n ? M::mul(L.B2, dnu_tot) : CT(0));
+      r.g.v[k] = Down<TG, CT>::cvt(dg);
+    }
+  }
+  template <int P>
+  static __device__ __forceinline__ void store(const Regs<P> &r, const Leaf &L, long long i) {
+    if (want_dg(L)) store_pack(L.dg + i, r.g);
+    if (want_dmu(L)) store_pack(L.dmu + i, r.dme);
+    if (want_dnu(L)) store_pack(L.dnu + i, r.dne);
+  }
+};
+
+// ---- the six out-of-place operators of the reference surface (single dtype T for every array) ----
+// Generic 2-in / 2-out shape; unused slots are compiled away through the NIN/NOUT constants.
+enum { OP_FWD_MU = 0, OP_FWD_NU, OP_FWD_UPD, OP_BWD_MU, OP_BWD_NU, OP_BWD_UPD };
+
+template <typename T, int KIND>
+struct UnfusedOp {
+  using CT = T;
+  static constexpr int NIN = (KIND == OP_BWD_MU) ? 1 : (KIND == OP_BWD_UPD ? 3 : 2);
+  static constexpr int NOUT = (KIND <= OP_FWD_UPD) ? 1 : 2;
+  static constexpr int NPTR = NIN + NOUT, NGS = 4, NLS = 2;
+  struct Leaf {
+    const T *in[3];
+    T *out[2];
+    CT s0, s1, s2, s3;
+  };
+  template <class Tab>
+  static __device__ __forceinline__ Leaf leaf(const Tab &t, int l) {
+    Leaf L;
+#pragma unroll
+    for (int a = 0; a < NIN; ++a) L.in[a] = (const T *)t.ptr[a][l];
+#pragma unroll
+    for (int a = 0; a < NOUT; ++a) L.out[a] = (T *)t.ptr[NIN + a][l];
+    L.s0 = t.gs[0], L.s1 = t.gs[1], L.s2 = t.gs[2], L.s3 = t.gs[3];
+    return L;
+  }
+  template <int P>
+  static __device__ __forceinline__ bool aligned(const Leaf &L) {
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < NIN; ++a) ok = ok && is_aligned<T, P>(L.in[a]);
+#pragma unroll
+    for (int a = 0; a < NOUT; ++a) ok = ok && is_aligned<T, P>(L.out[a]);
+    return ok;
+  }
+  template <int P>
+  struct Regs {
+    Pack<T, P> a[3];  // inputs; a[0], a[1] are overwritten with the outputs
+  };
+  template <int P>
+  static __device__ __forceinline__ void load(Regs<P> &r, const Leaf &L, long long i) {
+#pragma unroll
+    for (int a = 0; a < NIN; ++a) load_pack<true>(r.a[a], L.in[a] + i);
+  }
+  template <int P>
+  static __device__ __forceinline__ void compute(Regs<P> &r, const Leaf &L) {
+    using M = Math<CT>;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      if constexpr (KIND == OP_FWD_MU) {  // in: g, mu ; s0=B1 s1=OMB1                 (cpu.cpp:105)
+        r.a[0].v[k] = M::add(M::mul(L.s0, r.a[1].v[k]), M::mul(L.s1, r.a[0].v[k]));
+      } else if constexpr (KIND == OP_FWD_NU) {  // in: g, nu ; s0=B2 s1=OMB2          (cpu.cpp:140)
+        const T g = r.a[0].v[k];
+        r.a[0].v[k] = M::add(M::mul(L.s0, r.a[1].v[k]), M::mul(M::mul(L.s1, g), g));
+      } else if constexpr (KIND == OP_FWD_UPD) {  // in: mu', nu' ; s0=C1 s1=C2 s2=ER s3=EPS (cpu.cpp:176-179)
+        const T m_hat = M::mul(r.a[0].v[k], L.s0);
+        const T v_hat = M::mul(r.a[1].v[k], L.s1);
+        r.a[0].v[k] = M::div(m_hat, M::add(M::sqrt(M::add(v_hat, L.s2)), L.s3));
+      } else if constexpr (KIND == OP_BWD_MU) {  // in: dmu ; s0=B1 s1=OMB1 ; out: dg, dmu (cpu.cpp:223-224)
+        const T d = r.a[0].v[k];
+        r.a[0].v[k] = M::mul(L.s1, d);
+        r.a[1].v[k] = M::mul(L.s0, d);
+      } else if constexpr (KIND == OP_BWD_NU) {  // in: dnu, g ; s0=B2 s1=TWO_OMB2 ; out: dg, dnu (cpu.cpp:261-262)
+        const T d = r.a[0].v[k];
+        r.a[0].v[k] = M::mul(M::mul(L.s1, r.a[1].v[k]), d);
+        r.a[1].v[k] = M::mul(L.s0, d);
+      } else {  // OP_BWD_UPD  in: du, u, mu' ; s0=O1 s1=C2E ; out: dmu', dnu'         (cpu.cpp:298-316)
+        const T du = r.a[0].v[k], u = r.a[1].v[k], m = r.a[2].v[k];
+        T dm = T(0), dn = T(0);
+        if (m != T(0)) {
+          const T q = M::div(u, m);
+          const T den = M::mul(q, L.s0);
+          dm = M::mul(du, q);
+          const T t = M::mul(M::mul(-du, u), den);
+          dn = M::dnu_tail(t, L.s1, den);
+        }
+        r.a[0].v[k] = dm;
+        r.a[1].v[k] = dn;
+      }
+    }
+  }
+  template <int P>
+  static __device__ __forceinline__ void store(const Regs<P> &r, const Leaf &L, long long i) {
+#pragma unroll
+    for (int a = 0; a < NOUT; ++a) store_pack(L.out[a] + i, r.a[a]);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// the streaming engine
+// ------------------------------------------------------------------------------------------------
+template <class Op, int P, int U, int BLOCK>
+__device__ __forceinline__ void process_chunk(const typename Op::Leaf &L, long long off, int len) {
+  constexpr int TILE = BLOCK * P * U;
+  const int tid = threadIdx.x;
+  long long base = off;
+  int rem = len;
+  // full tiles: U front-batched vector loads per array, no bounds checks
+  for (; rem >= TILE; rem -= TILE, base += TILE) {
+    typename Op::template Regs<P> r[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) Op::template load<P>(r[j], L, base + (long long)(j * BLOCK + tid) * P);
+#pragma unroll
+    for (int j = 0; j < U; ++j) Op::template compute<P>(r[j], L);
+#pragma unroll
+    for (int j = 0; j < U; ++j) Op::template store<P>(r[j], L, base + (long long)(j * BLOCK + tid) * P);
+  }
+  // ragged end of the leaf: whole vectors, then < P single elements
+  const int nvec = rem / P;
+  for (int v = tid; v < nvec; v += BLOCK) {
+    typename Op::template Regs<P> r;
+    Op::template load<P>(r, L, base + (long long)v * P);
+    Op::template compute<P>(r, L);
+    Op::template store<P>(r, L, base + (long long)v * P);
+  }
+  if constexpr (P > 1) {
+    const int tail = rem - nvec * P;
+    if (tid < tail) {
+      typename Op::template Regs<1> r;
+      const long long i = base + (long long)nvec * P + tid;
+      Op::template load<1>(r, L, i);
+      Op::template compute<1>(r, L);
+      Op::template store<1>(r, L, i);
+    }
+  }
+}
+
+template <class Op, int P, int U, int BLOCK, int MAXL>
+__global__ void __launch_bounds__(BLOCK) stream_kernel(const __grid_constant__ Table<Op, MAXL> tab) {
+  for (int c = blockIdx.x; c < tab.total_chunks; c += gridDim.x) {
+    int l = 0;
+    if constexpr (MAXL > 1) {
+      // largest l with chunk_start[l] <= c (uniform across the CTA; constant-bank reads)
+      int lo = 0, hi = tab.num_leaves;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tab.chunk_start[mid] <= c) lo = mid; else hi = mid;
+      }
+      l = lo;
+    }
+    const typename Op::Leaf L = Op::leaf(tab, l);
+    const long long off = (long long)(c - tab.chunk_start[l]) * tab.chunk_elems;
+    const long long left = tab.n[l] - off;
+    const int len = left < (long long)tab.chunk_elems ? (int)left : tab.chunk_elems;
+    if (Op::template aligned<P>(L)) {
+      process_chunk<Op, P, U, BLOCK>(L, off, len);
+    } else {
+      process_chunk<Op, 1, 1, BLOCK>(L, off, len);  // unaligned views: element-wise path
+    }
+  }
+}
+
+}  // namespace b200adam

@@ -1,0 +1,530 @@
+// b200_adam.cu -- host side of libb200adam.so: the C ABI declared in include/b200_adam.h.
+//
+// Each entry point derives the host scalars exactly like the reference launchers do
+// (/root/reference/src/adam_op/adam_op_impl_cuda.cu:73-75,253-255,452-454 == adam_op_impl_cpu.cpp:72-74,
+// 190-192,327-329: std::pow in double, one rounding to the tensor dtype), fills a leaf table that travels in
+// the kernel parameters and launches ONE persistent streaming kernel (adam_kernels.cuh) on the caller's stream.
+#include "b200_adam.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "adam_kernels.cuh"
+
+namespace b200adam {
+
+// ---- launch configuration (chosen from the on-device sweep recorded in profiles/) ------------------
+// vector width P (elements), unroll U (vectors in flight per array per thread), CTA size.
+#ifndef B200_ADAM_BLOCK
+#define B200_ADAM_BLOCK 256
+#endif
+template <typename TG, typename TS>
+struct Cfg;  // fwd / bwd / unfused vector configs per dtype family
+// fp32 defaults can be overridden at compile time by the tuning sweep (tools/tune_sweep.py)
+#ifndef B200_P_FWD
+#define B200_P_FWD 8
+#endif
+#ifndef B200_U_FWD
+#define B200_U_FWD 2
+#endif
+#ifndef B200_P_BWD
+#define B200_P_BWD 8
+#endif
+#ifndef B200_U_BWD
+#define B200_U_BWD 1
+#endif
+template <>
+struct Cfg<float, float> {
+  static constexpr int P_FWD = B200_P_FWD, U_FWD = B200_U_FWD, P_BWD = B200_P_BWD, U_BWD = B200_U_BWD, P_UNF = 8,
+                       U_UNF = 2;
+};
+template <>
+struct Cfg<double, double> {
+  static constexpr int P_FWD = 4, U_FWD = 2, P_BWD = 4, U_BWD = 1, P_UNF = 4, U_UNF = 2;
+};
+template <>
+struct Cfg<bf16_t, float> {
+  static constexpr int P_FWD = 8, U_FWD = 2, P_BWD = 8, U_BWD = 1, P_UNF = 8, U_UNF = 2;
+};
+
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_ctas_per_sm{0};
+static std::atomic<int> g_tiles_per_chunk{0};
+
+struct DeviceInfo {
+  int sms = 0;
+  int cc_major = 0;
+};
+
+static int device_info(DeviceInfo *out) {
+  static DeviceInfo cache[64];
+  static std::atomic<int> ready[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= 64) return B200_ADAM_E_NO_DEVICE;
+  if (!ready[dev].load(std::memory_order_acquire)) {
+    DeviceInfo d;
+    e = cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return (int)e;
+    cache[dev] = d;
+    ready[dev].store(1, std::memory_order_release);
+  }
+  *out = cache[dev];
+  return 0;
+}
+
+// One host-side leaf handed to the generic launcher.
+template <class Op>
+struct HostLeaf {
+  void *ptr[Op::NPTR];
+  long long n;
+  typename Op::CT ls[Op::NLS > 0 ? Op::NLS : 1];
+};
+
+template <class Op, int P, int U, int BLOCK, int MAXL>
+static int occupancy_ctas_per_sm() {
+  static std::atomic<int> cached{0};
+  int v = cached.load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  int nb = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, stream_kernel<Op, P, U, BLOCK, MAXL>, BLOCK, 0);
+  if (e != cudaSuccess || nb <= 0) nb = 1;
+  cached.store(nb, std::memory_order_relaxed);
+  return nb;
+}
+
+template <class Op, int P, int U, int BLOCK>
+static int pick_chunk_elems(long long total_elems, int sms) {
+  constexpr int TILE = BLOCK * P * U;
+  int tiles = g_tiles_per_chunk.load(std::memory_order_relaxed);
+  if (tiles <= 0) tiles = 2;
+  // small problems: one tile per chunk so the work spreads over as many SMs as possible
+  if (total_elems < (long long)TILE * tiles * sms * 4) tiles = 1;
+  return TILE * tiles;
+}
+
+template <class Op, int P, int U, int BLOCK, int MAXL>
+static int launch_table(Table<Op, MAXL> &tab, const DeviceInfo &di, cudaStream_t stream) {
+  if (tab.total_chunks <= 0) return 0;
+  int per_sm = g_ctas_per_sm.load(std::memory_order_relaxed);
+  if (per_sm <= 0) per_sm = occupancy_ctas_per_sm<Op, P, U, BLOCK, MAXL>();
+  long long grid = (long long)di.sms * per_sm;
+  if (grid > tab.total_chunks) grid = tab.total_chunks;
+  stream_kernel<Op, P, U, BLOCK, MAXL><<<(unsigned)grid, BLOCK, 0, stream>>>(tab);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+// Feeds leaves (produced by `next(i, leaf)`, which returns false for a leaf to skip) through tables of
+// capacity MAXL, launching whenever a table is full.
+template <class Op, int P, int U, int BLOCK, int MAXL, class NextFn>
+static int run_batches(long long num_leaves, long long total_elems, int flags, const typename Op::CT *gs,
+                       NextFn &&next, cudaStream_t stream) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  Table<Op, MAXL> tab;
+  const int chunk = pick_chunk_elems<Op, P, U, BLOCK>(total_elems, di.sms);
+  auto reset = [&]() {
+    tab.num_leaves = 0;
+    tab.chunk_elems = chunk;
+    tab.total_chunks = 0;
+    tab.flags = flags;
+    for (int k = 0; k < Op::NGS; ++k) tab.gs[k] = gs[k];
+    tab.chunk_start[0] = 0;
+  };
+  reset();
+  for (long long i = 0; i < num_leaves; ++i) {
+    HostLeaf<Op> hl;
+    if (!next(i, hl)) continue;
+    long long off = 0;
+    // a leaf with more than INT_MAX/2 chunks is split into several table entries (keeps chunk ids in int)
+    while (off < hl.n) {
+      const long long max_elems = (long long)chunk * (1ll << 28);
+      const long long part = (hl.n - off < max_elems) ? (hl.n - off) : max_elems;
+      const long long nchunks = (part + chunk - 1) / chunk;
+      if (tab.num_leaves == MAXL || (long long)tab.total_chunks + nchunks > (1ll << 30)) {
+        if (int rc = launch_table<Op, P, U, BLOCK, MAXL>(tab, di, stream)) return rc;
+        reset();
+      }
+      const int l = tab.num_leaves++;
+      tab.n[l] = part;
+      for (int a = 0; a < Op::NPTR; ++a) tab.ptr[a][l] = hl.ptr[a];
+      for (int a = 0; a < Op::NLS; ++a) tab.ls[a][l] = hl.ls[a];
+      tab.total_chunks += (int)nchunks;
+      tab.chunk_start[l + 1] = tab.total_chunks;
+      off += part;
+      if (off < hl.n) {  // advance the pointers of the split leaf; element sizes are Op specific
+        Op::advance(hl.ptr, part);
+      }
+    }
+  }
+  return launch_table<Op, P, U, BLOCK, MAXL>(tab, di, stream);
+}
+
+template <class Op, int P, int U, class NextFn>
+static int run_op(long long num_leaves, long long total_elems, int flags, const typename Op::CT *gs, NextFn &&next,
+                  cudaStream_t stream) {
+  constexpr int BLOCK = B200_ADAM_BLOCK;
+  if (num_leaves <= 1) return run_batches<Op, P, U, BLOCK, 1>(num_leaves, total_elems, flags, gs, next, stream);
+  if (num_leaves <= 64) return run_batches<Op, P, U, BLOCK, 64>(num_leaves, total_elems, flags, gs, next, stream);
+  return run_batches<Op, P, U, BLOCK, 256>(num_leaves, total_elems, flags, gs, next, stream);
+}
+
+// ---- host wrappers that give every Op an `advance` (pointer bump for >2^28-chunk leaves) ------------
+template <typename TG, typename TS, typename CT, bool INPLACE>
+struct FwdH : FusedFwd<TG, TS, CT, INPLACE> {
+  static void advance(void **p, long long k) {
+    const size_t sz[6] = {sizeof(TG), sizeof(TS), sizeof(TS), sizeof(TS), sizeof(TS), sizeof(TG)};
+    for (int a = 0; a < 6; ++a)
+      if (p[a]) p[a] = (char *)p[a] + (size_t)k * sz[a];
+  }
+};
+template <typename TG, typename TS, typename CT, int MODE>
+struct BwdH : FusedBwd<TG, TS, CT, MODE> {
+  static void advance(void **p, long long k) {
+    const size_t sz[9] = {sizeof(TG), sizeof(TG), sizeof(TS), sizeof(TG), sizeof(TS),
+                          sizeof(TS), sizeof(TG), sizeof(TS), sizeof(TS)};
+    for (int a = 0; a < 9; ++a)
+      if (p[a]) p[a] = (char *)p[a] + (size_t)k * sz[a];
+  }
+};
+template <typename T, int KIND>
+struct UnfH : UnfusedOp<T, KIND> {
+  static void advance(void **p, long long k) {
+    for (int a = 0; a < UnfusedOp<T, KIND>::NPTR; ++a)
+      if (p[a]) p[a] = (char *)p[a] + (size_t)k * sizeof(T);
+  }
+};
+
+// ---- host scalars (the reference's derivation; see file header) -----------------------------------
+static inline double inv_one_minus_pow(double b, uint64_t count) { return 1 / (1 - std::pow(b, (double)count)); }
+static inline double one_minus_pow(double b, uint64_t count) { return 1 - std::pow(b, (double)count); }
+static inline double inv_one_minus_pow_eps(double b, double eps_root, uint64_t count) {
+  return 1 / (1 - std::pow(b, (double)count) + eps_root);
+}
+
+// ---- fused forward ---------------------------------------------------------------------------------
+template <typename TG, typename TS, typename CT, bool INPLACE>
+static int fused_forward_impl(int64_t L, const void *const *g, const void *const *mu, const void *const *nu,
+                              void *const *mu_out, void *const *nu_out, void *const *u_out, const int64_t *n,
+                              const uint64_t *count, double b1, double b2, double eps, double eps_root,
+                              cudaStream_t stream) {
+  using Op = FwdH<TG, TS, CT, INPLACE>;
+  const CT B1 = (CT)b1, B2 = (CT)b2;
+  const CT gs[6] = {B1, CT(1) - B1, B2, CT(1) - B2, (CT)eps_root, (CT)eps};
+  long long total = 0;
+  for (int64_t i = 0; i < L; ++i) {
+    if (n[i] < 0) return B200_ADAM_E_ARG;
+    if (n[i] > 0 && (!g[i] || !mu[i] || !nu[i] || !mu_out[i] || !nu_out[i] || !u_out[i])) return B200_ADAM_E_ARG;
+    total += n[i];
+  }
+  uint64_t last_count = ~0ull;
+  CT c1 = 0, c2 = 0;
+  auto next = [&](long long i, HostLeaf<Op> &hl) {
+    if (n[i] == 0) return false;
+    if (count[i] != last_count) {  // pow() once per distinct count
+      last_count = count[i];
+      c1 = (CT)inv_one_minus_pow(b1, last_count);
+      c2 = (CT)inv_one_minus_pow(b2, last_count);
+    }
+    hl.ptr[0] = const_cast<void *>(g[i]), hl.ptr[1] = const_cast<void *>(mu[i]), hl.ptr[2] = const_cast<void *>(nu[i]);
+    hl.ptr[3] = mu_out[i], hl.ptr[4] = nu_out[i], hl.ptr[5] = u_out[i];
+    hl.n = n[i];
+    hl.ls[0] = c1, hl.ls[1] = c2;
+    return true;
+  };
+  using C = Cfg<TG, TS>;
+  return run_op<Op, C::P_FWD, C::U_FWD>(L, total, 0, gs, next, stream);
+}
+
+template <bool INPLACE>
+static int fused_forward_dispatch(int dtype, int64_t L, const void *const *g, const void *const *mu,
+                                  const void *const *nu, void *const *mu_out, void *const *nu_out,
+                                  void *const *u_out, const int64_t *n, const uint64_t *count, double b1, double b2,
+                                  double eps, double eps_root, void *stream) {
+  if (L < 0) return B200_ADAM_E_ARG;
+  if (L == 0) return 0;
+  if (!g || !mu || !nu || !mu_out || !nu_out || !u_out || !n || !count) return B200_ADAM_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case B200_ADAM_F32:
+      return fused_forward_impl<float, float, float, INPLACE>(L, g, mu, nu, mu_out, nu_out, u_out, n, count, b1, b2,
+                                                              eps, eps_root, s);
+#ifndef B200_ADAM_TUNE_F32_ONLY
+    case B200_ADAM_F64:
+      return fused_forward_impl<double, double, double, INPLACE>(L, g, mu, nu, mu_out, nu_out, u_out, n, count, b1,
+                                                                 b2, eps, eps_root, s);
+    case B200_ADAM_BF16_F32:
+      return fused_forward_impl<bf16_t, float, float, INPLACE>(L, g, mu, nu, mu_out, nu_out, u_out, n, count, b1, b2,
+                                                               eps, eps_root, s);
+#endif
+    default:
+      return B200_ADAM_E_DTYPE;
+  }
+}
+
+// ---- fused backward --------------------------------------------------------------------------------
+template <typename TG, typename TS, typename CT, int MODE>
+static int fused_backward_mode(int64_t L, const void *const *du, const void *const *u, const void *const *new_mu,
+                               const void *const *g, const void *const *dmu_ext, const void *const *dnu_ext,
+                               void *const *dg, void *const *dmu, void *const *dnu, const int64_t *n,
+                               const uint64_t *count, double b1, double b2, double eps_root, long long total,
+                               cudaStream_t stream) {
+  using Op = BwdH<TG, TS, CT, MODE>;
+  const CT B1 = (CT)b1, B2 = (CT)b2;
+  const CT gs[4] = {B1, CT(1) - B1, B2, CT(2) * (CT(1) - B2)};
+  uint64_t last_count = ~0ull;
+  CT o1 = 0, c2e = 0;
+  auto next = [&](long long i, HostLeaf<Op> &hl) {
+    if (n[i] == 0) return false;
+    if (!dg[i] && !dmu[i] && !dnu[i]) return false;  // nothing to write
+    if (count[i] != last_count) {
+      last_count = count[i];
+      o1 = (CT)one_minus_pow(b1, last_count);
+      c2e = (CT)inv_one_minus_pow_eps(b2, eps_root, last_count);
+    }
+    const void *p[9] = {du[i], u[i], new_mu[i], g[i], dmu_ext[i], dnu_ext[i], dg[i], dmu[i], dnu[i]};
+    for (int a = 0; a < 9; ++a) hl.ptr[a] = const_cast<void *>(p[a]);
+    hl.n = n[i];
+    hl.ls[0] = o1, hl.ls[1] = c2e;
+    return true;
+  };
+  using C = Cfg<TG, TS>;
+  return run_op<Op, C::P_BWD, C::U_BWD>(L, total, 0, gs, next, stream);
+}
+
+template <typename TG, typename TS, typename CT>
+static int fused_backward_impl(int64_t L, const void *const *du, const void *const *u, const void *const *new_mu,
+                               const void *const *g, const void *const *dmu_ext, const void *const *dnu_ext,
+                               void *const *dg, void *const *dmu, void *const *dnu, const int64_t *n,
+                               const uint64_t *count, double b1, double b2, double eps_root, cudaStream_t stream) {
+  bool all_full = true, all_last = true;
+  long long total = 0;
+  for (int64_t i = 0; i < L; ++i) {
+    if (n[i] < 0) return B200_ADAM_E_ARG;
+    if (n[i] == 0) continue;
+    total += n[i];
+    const bool hdu = du[i] != nullptr, hme = dmu_ext[i] != nullptr, hne = dnu_ext[i] != nullptr;
+    if (hdu && (!u[i] || !new_mu[i])) return B200_ADAM_E_ARG;
+    if (dg[i] && (hdu || hne) && !g[i]) return B200_ADAM_E_ARG;
+    const bool outs = dg[i] && dmu[i] && dnu[i];
+    all_full = all_full && hdu && hme && hne && outs;
+    all_last = all_last && hdu && !hme && !hne && outs;
+  }
+  if (total == 0) return 0;
+  if (all_full)
+    return fused_backward_mode<TG, TS, CT, BWD_FULL>(L, du, u, new_mu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n, count,
+                                                     b1, b2, eps_root, total, stream);
+  if (all_last)
+    return fused_backward_mode<TG, TS, CT, BWD_LAST>(L, du, u, new_mu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n, count,
+                                                     b1, b2, eps_root, total, stream);
+  return fused_backward_mode<TG, TS, CT, BWD_GENERIC>(L, du, u, new_mu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n, count,
+                                                      b1, b2, eps_root, total, stream);
+}
+
+// ---- un-fused single-tensor operators --------------------------------------------------------------
+template <typename T, int KIND>
+static int unfused_impl(const void *in0, const void *in1, const void *in2, void *out0, void *out1, int64_t n,
+                        const T (&gs)[4], cudaStream_t stream) {
+  using Op = UnfH<T, KIND>;
+  if (n < 0) return B200_ADAM_E_ARG;
+  if (n == 0) return 0;
+  const void *ins[3] = {in0, in1, in2};
+  void *outs[2] = {out0, out1};
+  for (int a = 0; a < Op::NIN; ++a)
+    if (!ins[a]) return B200_ADAM_E_ARG;
+  for (int a = 0; a < Op::NOUT; ++a)
+    if (!outs[a]) return B200_ADAM_E_ARG;
+  auto next = [&](long long, HostLeaf<Op> &hl) {
+    for (int a = 0; a < Op::NIN; ++a) hl.ptr[a] = const_cast<void *>(ins[a]);
+    for (int a = 0; a < Op::NOUT; ++a) hl.ptr[Op::NIN + a] = outs[a];
+    hl.n = n;
+    hl.ls[0] = hl.ls[1] = T(0);
+    return true;
+  };
+  using C = Cfg<T, T>;
+  return run_op<Op, C::P_UNF, C::U_UNF>(1, n, 0, gs, next, stream);
+}
+
+#ifdef B200_ADAM_TUNE_F32_ONLY
+#define B200_UNFUSED_DISPATCH(KIND, in0, in1, in2, out0, out1, s0, s1, s2, s3) return B200_ADAM_E_DTYPE;
+#else
+#define B200_UNFUSED_DISPATCH(KIND, in0, in1, in2, out0, out1, s0, s1, s2, s3)                          \
+  switch (dtype) {                                                                                      \
+    case B200_ADAM_F32: {                                                                               \
+      const float gs[4] = {(float)(s0), (float)(s1), (float)(s2), (float)(s3)};                         \
+      return unfused_impl<float, KIND>(in0, in1, in2, out0, out1, n, gs, (cudaStream_t)stream);         \
+    }                                                                                                   \
+    case B200_ADAM_F64: {                                                                               \
+      const double gs[4] = {(double)(s0), (double)(s1), (double)(s2), (double)(s3)};                    \
+      return unfused_impl<double, KIND>(in0, in1, in2, out0, out1, n, gs, (cudaStream_t)stream);        \
+    }                                                                                                   \
+    default:                                                                                            \
+      return B200_ADAM_E_DTYPE;                                                                         \
+  }
+#endif
+
+// `1 - rn_T(b)` must be formed in T from the rounded beta (adam_op_impl_cpu.cpp:105,140,223,261).
+template <typename T>
+static inline T omb(double b) {
+  return T(1) - (T)b;
+}
+
+}  // namespace b200adam
+
+using namespace b200adam;
+
+extern "C" {
+
+int b200_adam_abi_version(void) { return B200_ADAM_ABI_VERSION; }
+
+const char *b200_adam_error_string(int code) {
+  switch (code) {
+    case B200_ADAM_OK: return "ok";
+    case B200_ADAM_E_DTYPE: return "b200_adam: dtype not supported by this entry point";
+    case B200_ADAM_E_ARG: return "b200_adam: invalid argument (NULL array, negative size or missing saved tensor)";
+    case B200_ADAM_E_NO_DEVICE: return "b200_adam: no usable CUDA device";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "b200_adam: unknown error";
+}
+
+uint64_t b200_adam_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int b200_adam_set_tuning(int ctas_per_sm, int tiles_per_chunk) {
+  if (ctas_per_sm < 0 || tiles_per_chunk < 0) return B200_ADAM_E_ARG;
+  g_ctas_per_sm.store(ctas_per_sm);
+  g_tiles_per_chunk.store(tiles_per_chunk);
+  return 0;
+}
+
+int b200_adam_query_launch(int dtype, int backward, int64_t n, int32_t out[5]) {
+  if (!out || n < 0) return B200_ADAM_E_ARG;
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  constexpr int BLOCK = B200_ADAM_BLOCK;
+  int P, U, occ, chunk;
+#define B200_Q(TG, TS, CT)                                                                                    \
+  if (backward) {                                                                                             \
+    using Op = BwdH<TG, TS, CT, BWD_FULL>;                                                                    \
+    P = Cfg<TG, TS>::P_BWD, U = Cfg<TG, TS>::U_BWD;                                                           \
+    occ = occupancy_ctas_per_sm<Op, Cfg<TG, TS>::P_BWD, Cfg<TG, TS>::U_BWD, BLOCK, 1>();                      \
+    chunk = pick_chunk_elems<Op, Cfg<TG, TS>::P_BWD, Cfg<TG, TS>::U_BWD, BLOCK>(n, di.sms);                   \
+  } else {                                                                                                    \
+    using Op = FwdH<TG, TS, CT, false>;                                                                       \
+    P = Cfg<TG, TS>::P_FWD, U = Cfg<TG, TS>::U_FWD;                                                           \
+    occ = occupancy_ctas_per_sm<Op, Cfg<TG, TS>::P_FWD, Cfg<TG, TS>::U_FWD, BLOCK, 1>();                      \
+    chunk = pick_chunk_elems<Op, Cfg<TG, TS>::P_FWD, Cfg<TG, TS>::U_FWD, BLOCK>(n, di.sms);                   \
+  }
+  switch (dtype) {
+    case B200_ADAM_F32: B200_Q(float, float, float) break;
+#ifndef B200_ADAM_TUNE_F32_ONLY
+    case B200_ADAM_F64: B200_Q(double, double, double) break;
+    case B200_ADAM_BF16_F32: B200_Q(bf16_t, float, float) break;
+#endif
+    default: return B200_ADAM_E_DTYPE;
+  }
+#undef B200_Q
+  int per_sm = g_ctas_per_sm.load();
+  if (per_sm <= 0) per_sm = occ;
+  long long chunks = (n + chunk - 1) / chunk;
+  long long grid = (long long)di.sms * per_sm;
+  if (grid > chunks) grid = chunks;
+  out[0] = (int32_t)grid, out[1] = BLOCK, out[2] = chunk, out[3] = P, out[4] = U;
+  return 0;
+}
+
+int b200_adam_fused_forward(int dtype, int64_t num_leaves, const void *const *g, const void *const *mu,
+                            const void *const *nu, void *const *mu_out, void *const *nu_out, void *const *u_out,
+                            const int64_t *n, const uint64_t *count, double b1, double b2, double eps,
+                            double eps_root, void *stream) {
+  return fused_forward_dispatch<false>(dtype, num_leaves, g, mu, nu, mu_out, nu_out, u_out, n, count, b1, b2, eps,
+                                       eps_root, stream);
+}
+
+int b200_adam_forward_inplace_mt(int dtype, int64_t num_leaves, void *const *updates, void *const *mu,
+                                 void *const *nu, const int64_t *n, const uint64_t *count, double b1, double b2,
+                                 double eps, double eps_root, void *stream) {
+  return fused_forward_dispatch<true>(dtype, num_leaves, updates, mu, nu, mu, nu, updates, n, count, b1, b2, eps,
+                                      eps_root, stream);
+}
+
+int b200_adam_forward_inplace(int dtype, void *updates, void *mu, void *nu, int64_t n, double b1, double b2,
+                              double eps, double eps_root, uint64_t count, void *stream) {
+  return b200_adam_forward_inplace_mt(dtype, 1, &updates, &mu, &nu, &n, &count, b1, b2, eps, eps_root, stream);
+}
+
+int b200_adam_fused_backward(int dtype, int64_t num_leaves, const void *const *du, const void *const *u,
+                             const void *const *new_mu, const void *const *g, const void *const *dmu_ext,
+                             const void *const *dnu_ext, void *const *dg, void *const *dmu, void *const *dnu,
+                             const int64_t *n, const uint64_t *count, double b1, double b2, double eps_root,
+                             void *stream) {
+  if (num_leaves < 0) return B200_ADAM_E_ARG;
+  if (num_leaves == 0) return 0;
+  if (!du || !u || !new_mu || !g || !dmu_ext || !dnu_ext || !dg || !dmu || !dnu || !n || !count)
+    return B200_ADAM_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case B200_ADAM_F32:
+      return fused_backward_impl<float, float, float>(num_leaves, du, u, new_mu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n,
+                                                      count, b1, b2, eps_root, s);
+#ifndef B200_ADAM_TUNE_F32_ONLY
+    case B200_ADAM_F64:
+      return fused_backward_impl<double, double, double>(num_leaves, du, u, new_mu, g, dmu_ext, dnu_ext, dg, dmu, dnu,
+                                                         n, count, b1, b2, eps_root, s);
+    case B200_ADAM_BF16_F32:
+      return fused_backward_impl<bf16_t, float, float>(num_leaves, du, u, new_mu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n,
+                                                       count, b1, b2, eps_root, s);
+#endif
+    default:
+      return B200_ADAM_E_DTYPE;
+  }
+}
+
+int b200_adam_forward_mu(int dtype, const void *updates, const void *mu, void *mu_out, int64_t n, double b1,
+                         void *stream) {
+  B200_UNFUSED_DISPATCH(OP_FWD_MU, updates, mu, nullptr, mu_out, nullptr, b1,
+                        (dtype == B200_ADAM_F32 ? (double)omb<float>(b1) : omb<double>(b1)), 0, 0)
+}
+
+int b200_adam_forward_nu(int dtype, const void *updates, const void *nu, void *nu_out, int64_t n, double b2,
+                         void *stream) {
+  B200_UNFUSED_DISPATCH(OP_FWD_NU, updates, nu, nullptr, nu_out, nullptr, b2,
+                        (dtype == B200_ADAM_F32 ? (double)omb<float>(b2) : omb<double>(b2)), 0, 0)
+}
+
+int b200_adam_forward_updates(int dtype, const void *new_mu, const void *new_nu, void *updates_out, int64_t n,
+                              double b1, double b2, double eps, double eps_root, uint64_t count, void *stream) {
+  const double c1 = inv_one_minus_pow(b1, count), c2 = inv_one_minus_pow(b2, count);
+  B200_UNFUSED_DISPATCH(OP_FWD_UPD, new_mu, new_nu, nullptr, updates_out, nullptr, c1, c2, eps_root, eps)
+}
+
+int b200_adam_backward_mu(int dtype, const void *dmu, void *dupdates_out, void *dmu_out, int64_t n, double b1,
+                          void *stream) {
+  B200_UNFUSED_DISPATCH(OP_BWD_MU, dmu, nullptr, nullptr, dupdates_out, dmu_out, b1,
+                        (dtype == B200_ADAM_F32 ? (double)omb<float>(b1) : omb<double>(b1)), 0, 0)
+}
+
+int b200_adam_backward_nu(int dtype, const void *dnu, const void *updates, void *dupdates_out, void *dnu_out,
+                          int64_t n, double b2, void *stream) {
+  // TWO_OMB2 = T(2) * (T(1) - rn_T(b2)) is exact in T
+  B200_UNFUSED_DISPATCH(OP_BWD_NU, dnu, updates, nullptr, dupdates_out, dnu_out, b2,
+                        (dtype == B200_ADAM_F32 ? (double)(2.0f * omb<float>(b2)) : 2.0 * omb<double>(b2)), 0, 0)
+}
+
+int b200_adam_backward_updates(int dtype, const void *dupdates, const void *updates, const void *new_mu,
+                               void *dnew_mu_out, void *dnew_nu_out, int64_t n, double b1, double b2,
+                               double eps_root, uint64_t count, void *stream) {
+  (void)b2;
+  const double o1 = one_minus_pow(b1, count), c2e = inv_one_minus_pow_eps(b2, eps_root, count);
+  B200_UNFUSED_DISPATCH(OP_BWD_UPD, dupdates, updates, new_mu, dnew_mu_out, dnew_nu_out, o1, c2e, 0, 0)
+}
+
+}  // extern "C"

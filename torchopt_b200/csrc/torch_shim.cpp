@@ -1,0 +1,345 @@
+// torch_shim.cpp -- the CPython module `_C` (submodule `adam_op`) over the C ABI of libb200adam.so.
+//
+// This is the reference-side binding: it has the Python-visible surface of the reference's pybind module
+// (/root/reference/src/adam_op/adam_op.cpp:155-215, src/extension.cpp:20 -- same function names, keyword
+// names incl. backward_nu's misnamed `b1`, list return types, size_t `count` accepting a 0-dim tensor through
+// __index__) and the dispatcher's behaviour (/root/reference/src/adam_op/adam_op.cpp:32-153: .contiguous()
+// on the incoming gradient of the three backward ops only, fresh empty_like outputs, no shape/layout checks,
+// `throw std::runtime_error("Not implemented")` for devices without a kernel).  It owns nothing numeric:
+// it resolves device guard + current stream, allocates outputs and passes raw pointers across the C ABI.
+//
+// This build has NO CPU kernels: CPU (and meta, ...) tensors raise "Not implemented".
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+#include <torch/extension.h>
+
+#include <array>
+#include <map>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "b200_adam.h"
+
+namespace py = pybind11;
+using at::Tensor;
+using OptTensor = std::optional<Tensor>;
+
+namespace {
+
+[[noreturn]] void fail(int rc, const char *what) {
+  throw std::runtime_error(std::string(what) + ": " + b200_adam_error_string(rc));
+}
+
+inline void check(int rc, const char *what) {
+  if (rc != 0) fail(rc, what);
+}
+
+inline void require_cuda(const Tensor &t) {
+  // same contract as the reference dispatcher for a device it has no kernel for (adam_op.cpp:48)
+  if (!t.device().is_cuda()) throw std::runtime_error("Not implemented");
+}
+
+// element-type family of a call: `grad_like` is an updates/dupdates-side tensor, `state_like` a moment-side one
+int family(const Tensor &grad_like, const Tensor &state_like, const char *name, bool allow_mixed) {
+  const auto g = grad_like.scalar_type(), s = state_like.scalar_type();
+  if (g == at::kFloat && s == at::kFloat) return B200_ADAM_F32;
+  if (g == at::kDouble && s == at::kDouble) return B200_ADAM_F64;
+  if (allow_mixed && g == at::kBFloat16 && s == at::kFloat) return B200_ADAM_BF16_F32;
+  if (g != s) {
+    throw std::runtime_error(std::string("expected scalar type ") + c10::toString(g) + " but found " +
+                             c10::toString(s));
+  }
+  // message format of the ATen dispatch macro the reference relies on (include/common.h:26-37)
+  throw std::runtime_error(std::string("\"") + name + "\" not implemented for '" + c10::toString(g) + "'");
+}
+
+inline void same_type(const Tensor &a, const Tensor &b) {
+  if (a.scalar_type() != b.scalar_type())
+    throw std::runtime_error(std::string("expected scalar type ") + c10::toString(a.scalar_type()) +
+                             " but found " + c10::toString(b.scalar_type()));
+}
+
+struct Ctx {
+  c10::cuda::CUDAGuard guard;
+  void *stream;
+  explicit Ctx(const Tensor &t)
+      : guard(t.device()), stream((void *)c10::cuda::getCurrentCUDAStream(t.device().index()).stream()) {}
+};
+
+// ---- the seven reference operators ---------------------------------------------------------------
+std::array<Tensor, 3> forward_inplace(const Tensor &updates, const Tensor &mu, const Tensor &nu, double b1,
+                                      double b2, double eps, double eps_root, size_t count) {
+  require_cuda(updates);
+  const int dt = family(updates, mu, "adamForwardInplaceCUDA", true);
+  same_type(mu, nu);
+  Ctx c(updates);
+  check(b200_adam_forward_inplace(dt, updates.data_ptr(), mu.data_ptr(), nu.data_ptr(), updates.numel(), b1, b2,
+                                  eps, eps_root, count, c.stream),
+        "forward_");
+  return {updates, mu, nu};
+}
+
+Tensor forward_mu(const Tensor &updates, const Tensor &mu, double b1) {
+  require_cuda(updates);
+  const int dt = family(updates, mu, "adamForwardMuCUDA", false);
+  Ctx c(updates);
+  Tensor out = at::empty_like(mu);
+  check(b200_adam_forward_mu(dt, updates.data_ptr(), mu.data_ptr(), out.data_ptr(), updates.numel(), b1, c.stream),
+        "forward_mu");
+  return out;
+}
+
+Tensor forward_nu(const Tensor &updates, const Tensor &nu, double b2) {
+  require_cuda(updates);
+  const int dt = family(updates, nu, "adamForwardNuCUDA", false);
+  Ctx c(updates);
+  Tensor out = at::empty_like(nu);
+  check(b200_adam_forward_nu(dt, updates.data_ptr(), nu.data_ptr(), out.data_ptr(), updates.numel(), b2, c.stream),
+        "forward_nu");
+  return out;
+}
+
+Tensor forward_updates(const Tensor &new_mu, const Tensor &new_nu, double b1, double b2, double eps,
+                       double eps_root, size_t count) {
+  require_cuda(new_mu);
+  const int dt = family(new_mu, new_nu, "adamForwardUpdatesCUDA", false);
+  Ctx c(new_mu);
+  Tensor out = at::empty_like(new_mu);
+  check(b200_adam_forward_updates(dt, new_mu.data_ptr(), new_nu.data_ptr(), out.data_ptr(), new_mu.numel(), b1, b2,
+                                  eps, eps_root, count, c.stream),
+        "forward_updates");
+  return out;
+}
+
+std::array<Tensor, 2> backward_mu(const Tensor &dmu_in, const Tensor &updates, const Tensor &mu, double b1) {
+  require_cuda(dmu_in);
+  const Tensor dmu = dmu_in.contiguous();
+  const int dt = family(dmu, dmu, "adamBackwardMuCUDA", false);
+  Ctx c(dmu);
+  Tensor dupdates_out = at::empty_like(updates), dmu_out = at::empty_like(mu);
+  same_type(dmu, dupdates_out), same_type(dmu, dmu_out);
+  check(b200_adam_backward_mu(dt, dmu.data_ptr(), dupdates_out.data_ptr(), dmu_out.data_ptr(), dmu.numel(), b1,
+                              c.stream),
+        "backward_mu");
+  return {dupdates_out, dmu_out};
+}
+
+std::array<Tensor, 2> backward_nu(const Tensor &dnu_in, const Tensor &updates, const Tensor &nu, double b2) {
+  require_cuda(dnu_in);
+  const Tensor dnu = dnu_in.contiguous();
+  const int dt = family(dnu, updates, "adamForwardNuCUDA" /* sic: adam_op_impl_cuda.cu:382 */, false);
+  Ctx c(dnu);
+  Tensor dupdates_out = at::empty_like(updates), dnu_out = at::empty_like(nu);
+  same_type(dnu, dnu_out);
+  check(b200_adam_backward_nu(dt, dnu.data_ptr(), updates.data_ptr(), dupdates_out.data_ptr(), dnu_out.data_ptr(),
+                              dnu.numel(), b2, c.stream),
+        "backward_nu");
+  return {dupdates_out, dnu_out};
+}
+
+std::array<Tensor, 2> backward_updates(const Tensor &dupdates_in, const Tensor &updates, const Tensor &new_mu,
+                                       const Tensor &new_nu, double b1, double b2, double eps_root, size_t count) {
+  require_cuda(dupdates_in);
+  const Tensor dupdates = dupdates_in.contiguous();
+  const int dt = family(dupdates, updates, "adamBackwardUpdatesCUDA", false);
+  same_type(dupdates, new_mu);
+  Ctx c(dupdates);
+  Tensor dmu_out = at::empty_like(new_mu), dnu_out = at::empty_like(new_nu);
+  same_type(dupdates, dnu_out);
+  check(b200_adam_backward_updates(dt, dupdates.data_ptr(), updates.data_ptr(), new_mu.data_ptr(), dmu_out.data_ptr(),
+                                   dnu_out.data_ptr(), dupdates.numel(), b1, b2, eps_root, count, c.stream),
+        "backward_updates");
+  return {dmu_out, dnu_out};
+}
+
+// ---- fused multi-tensor operators (new) ------------------------------------------------------------
+struct GroupKey {
+  int device, dtype;
+  bool operator<(const GroupKey &o) const { return std::tie(device, dtype) < std::tie(o.device, o.dtype); }
+};
+
+// (new_mu, new_nu, new_updates) for every leaf; leaves whose `updates` is None yield (mu, nu, None), like
+// AdamOp.__call__ (accelerated_op/adam_op.py:148-149).  One launch per (device, dtype family).
+std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<OptTensor>> fused_forward(
+    const std::vector<OptTensor> &updates, const std::vector<Tensor> &mu, const std::vector<Tensor> &nu, double b1,
+    double b2, double eps, double eps_root, const std::vector<size_t> &count, bool inplace) {
+  const size_t L = updates.size();
+  if (mu.size() != L || nu.size() != L || count.size() != L)
+    throw std::runtime_error("fused_forward: updates, mu, nu and count must have the same number of leaves");
+  std::vector<Tensor> new_mu(L), new_nu(L);
+  std::vector<OptTensor> new_u(L);
+  std::map<GroupKey, std::vector<size_t>> groups;
+  for (size_t i = 0; i < L; ++i) {
+    if (!updates[i].has_value()) {
+      new_mu[i] = mu[i], new_nu[i] = nu[i];
+      continue;
+    }
+    const Tensor &g = *updates[i];
+    require_cuda(g);
+    const int dt = family(g, mu[i], inplace ? "adamForwardInplaceCUDA" : "adamForwardMuCUDA", true);
+    same_type(mu[i], nu[i]);
+    groups[GroupKey{(int)g.device().index(), dt}].push_back(i);
+  }
+  for (auto &kv : groups) {
+    const auto &idx = kv.second;
+    const size_t G = idx.size();
+    std::vector<const void *> pg(G), pmu(G), pnu(G);
+    std::vector<void *> omu(G), onu(G), ou(G);
+    std::vector<int64_t> n(G);
+    std::vector<uint64_t> cnt(G);
+    Ctx c(*updates[idx[0]]);
+    for (size_t k = 0; k < G; ++k) {
+      const size_t i = idx[k];
+      const Tensor &g = *updates[i];
+      if (inplace) {
+        new_mu[i] = mu[i], new_nu[i] = nu[i], new_u[i] = g;
+      } else {
+        new_mu[i] = at::empty_like(mu[i]), new_nu[i] = at::empty_like(nu[i]), new_u[i] = at::empty_like(g);
+      }
+      pg[k] = g.data_ptr(), pmu[k] = mu[i].data_ptr(), pnu[k] = nu[i].data_ptr();
+      omu[k] = new_mu[i].data_ptr(), onu[k] = new_nu[i].data_ptr(), ou[k] = new_u[i]->data_ptr();
+      n[k] = g.numel(), cnt[k] = count[i];
+    }
+    if (inplace) {
+      check(b200_adam_forward_inplace_mt(kv.first.dtype, (int64_t)G, ou.data(), omu.data(), onu.data(), n.data(),
+                                         cnt.data(), b1, b2, eps, eps_root, c.stream),
+            "forward_ (multi-tensor)");
+    } else {
+      check(b200_adam_fused_forward(kv.first.dtype, (int64_t)G, pg.data(), pmu.data(), pnu.data(), omu.data(),
+                                    onu.data(), ou.data(), n.data(), cnt.data(), b1, b2, eps, eps_root, c.stream),
+            "fused_forward");
+    }
+  }
+  return {new_mu, new_nu, new_u};
+}
+
+// Per leaf i: gradients (dupdates[i], dmu_ext[i], dnu_ext[i]) of (new_updates, new_mu, new_nu) -- any may be
+// None -- and the saved (new_updates[i], new_mu[i], g[i]).  need_* say which input gradients autograd wants.
+// Returns (dg, dmu, dnu) lists with None where not needed or where no gradient flows at all.
+std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor>> fused_backward(
+    const std::vector<OptTensor> &dupdates, const std::vector<OptTensor> &dmu_ext,
+    const std::vector<OptTensor> &dnu_ext, const std::vector<Tensor> &new_updates, const std::vector<Tensor> &new_mu,
+    const std::vector<Tensor> &g, const std::vector<bool> &need_dg, const std::vector<bool> &need_dmu,
+    const std::vector<bool> &need_dnu, double b1, double b2, double eps_root, const std::vector<size_t> &count) {
+  const size_t L = g.size();
+  if (dupdates.size() != L || dmu_ext.size() != L || dnu_ext.size() != L || new_updates.size() != L ||
+      new_mu.size() != L || need_dg.size() != L || need_dmu.size() != L || need_dnu.size() != L || count.size() != L)
+    throw std::runtime_error("fused_backward: all per-leaf lists must have the same length");
+  std::vector<OptTensor> dg(L), dmu(L), dnu(L);
+  std::vector<Tensor> cdu(L), cme(L), cne(L);  // keep the .contiguous() copies alive until after the launch
+  std::map<GroupKey, std::vector<size_t>> groups;
+  for (size_t i = 0; i < L; ++i) {
+    const bool hdu = dupdates[i].has_value(), hme = dmu_ext[i].has_value(), hne = dnu_ext[i].has_value();
+    if (!hdu && !hme && !hne) continue;  // nothing flows: all three stay None
+    const bool wg = need_dg[i] && (hdu || hme || hne), wm = need_dmu[i] && (hdu || hme), wn = need_dnu[i] && (hdu || hne);
+    if (!wg && !wm && !wn) continue;
+    require_cuda(g[i]);
+    const int dt = family(g[i], new_mu[i], "adamBackwardUpdatesCUDA", true);
+    if (hdu) cdu[i] = dupdates[i]->contiguous(), same_type(cdu[i], g[i]);
+    if (hme) cme[i] = dmu_ext[i]->contiguous(), same_type(cme[i], new_mu[i]);
+    if (hne) cne[i] = dnu_ext[i]->contiguous(), same_type(cne[i], new_mu[i]);
+    if (wg) dg[i] = at::empty_like(g[i]);
+    if (wm) dmu[i] = at::empty_like(new_mu[i]);
+    if (wn) dnu[i] = at::empty_like(new_mu[i]);
+    groups[GroupKey{(int)g[i].device().index(), dt}].push_back(i);
+  }
+  for (auto &kv : groups) {
+    const auto &idx = kv.second;
+    const size_t G = idx.size();
+    std::vector<const void *> pdu(G), pu(G), pm(G), pg(G), pme(G), pne(G);
+    std::vector<void *> odg(G), odm(G), odn(G);
+    std::vector<int64_t> n(G);
+    std::vector<uint64_t> cnt(G);
+    Ctx c(g[idx[0]]);
+    for (size_t k = 0; k < G; ++k) {
+      const size_t i = idx[k];
+      pdu[k] = cdu[i].defined() ? cdu[i].data_ptr() : nullptr;
+      pme[k] = cme[i].defined() ? cme[i].data_ptr() : nullptr;
+      pne[k] = cne[i].defined() ? cne[i].data_ptr() : nullptr;
+      pu[k] = new_updates[i].data_ptr(), pm[k] = new_mu[i].data_ptr(), pg[k] = g[i].data_ptr();
+      odg[k] = dg[i] ? dg[i]->data_ptr() : nullptr;
+      odm[k] = dmu[i] ? dmu[i]->data_ptr() : nullptr;
+      odn[k] = dnu[i] ? dnu[i]->data_ptr() : nullptr;
+      n[k] = g[i].numel(), cnt[k] = count[i];
+    }
+    check(b200_adam_fused_backward(kv.first.dtype, (int64_t)G, pdu.data(), pu.data(), pm.data(), pg.data(), pme.data(),
+                                   pne.data(), odg.data(), odm.data(), odn.data(), n.data(), cnt.data(), b1, b2,
+                                   eps_root, c.stream),
+          "fused_backward");
+  }
+  return {dg, dmu, dnu};
+}
+
+// host-buffer step (CPU tensors in, CPU tensors out, work done on the current CUDA device)
+std::array<Tensor, 6> host_step(const Tensor &g, const Tensor &mu, const Tensor &nu, const Tensor &du,
+                                const Tensor &dmu_ext, const Tensor &dnu_ext, std::array<Tensor, 6> out, double b1,
+                                double b2, double eps, double eps_root, size_t count, int64_t slice_elems) {
+  const Tensor *ins[6] = {&g, &mu, &nu, &du, &dmu_ext, &dnu_ext};
+  for (int a = 0; a < 6; ++a) {
+    if (!ins[a]->device().is_cpu() || !out[a].device().is_cpu() || ins[a]->scalar_type() != at::kFloat ||
+        out[a].scalar_type() != at::kFloat || !ins[a]->is_contiguous() || !out[a].is_contiguous() ||
+        ins[a]->numel() != g.numel() || out[a].numel() != g.numel())
+      throw std::runtime_error("host_step: expects contiguous float32 CPU tensors of equal numel");
+  }
+  int rc;
+  {
+    py::gil_scoped_release nogil;
+    rc = b200_adam_host_step_f32(g.data_ptr<float>(), mu.data_ptr<float>(), nu.data_ptr<float>(), du.data_ptr<float>(),
+                                 dmu_ext.data_ptr<float>(), dnu_ext.data_ptr<float>(), out[0].data_ptr<float>(),
+                                 out[1].data_ptr<float>(), out[2].data_ptr<float>(), out[3].data_ptr<float>(),
+                                 out[4].data_ptr<float>(), out[5].data_ptr<float>(), g.numel(), b1, b2, eps, eps_root,
+                                 count, slice_elems);
+  }
+  check(rc, "host_step");
+  return out;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(_C, mod) {
+  mod.doc() = "torchopt_b200 native module: B200 (sm_100a) accelerated differentiable Adam";
+  py::module m = mod.def_submodule("adam_op", "Adam Ops");
+  // -- the reference surface: names, keyword names and order as in adam_op.cpp:157-214
+  m.def("forward_", &forward_inplace, "Adam forward inplace", py::arg("updates"), py::arg("mu"), py::arg("nu"),
+        py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("count"));
+  m.def("forward_mu", &forward_mu, "Adam forward mu", py::arg("updates"), py::arg("mu"), py::arg("b1"));
+  m.def("forward_nu", &forward_nu, "Adam forward nu", py::arg("updates"), py::arg("nu"), py::arg("b2"));
+  m.def("forward_updates", &forward_updates, "Adam forward updates", py::arg("new_mu"), py::arg("new_nu"),
+        py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("count"));
+  m.def("backward_mu", &backward_mu, "Adam backward mu", py::arg("dmu"), py::arg("updates"), py::arg("mu"),
+        py::arg("b1"));
+  m.def("backward_nu", &backward_nu, "Adam backward nu", py::arg("dnu"), py::arg("updates"), py::arg("nu"),
+        py::arg("b1"));
+  m.def("backward_updates", &backward_updates, "Adam backward updates", py::arg("dupdates"), py::arg("updates"),
+        py::arg("new_mu"), py::arg("new_nu"), py::arg("b1"), py::arg("b2"), py::arg("eps_root"), py::arg("count"));
+  // -- new: fused, multi-tensor
+  m.def("fused_forward", &fused_forward, "Fused differentiable Adam forward over all leaves (one launch)",
+        py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("b1"), py::arg("b2"), py::arg("eps"),
+        py::arg("eps_root"), py::arg("count"), py::arg("inplace") = false);
+  m.def("fused_backward", &fused_backward, "Fused differentiable Adam backward over all leaves (one launch)",
+        py::arg("dupdates"), py::arg("dmu_ext"), py::arg("dnu_ext"), py::arg("new_updates"), py::arg("new_mu"),
+        py::arg("updates"), py::arg("need_dupdates"), py::arg("need_dmu"), py::arg("need_dnu"), py::arg("b1"),
+        py::arg("b2"), py::arg("eps_root"), py::arg("count"));
+  m.def("host_step", &host_step, "Fused forward+backward over pinned HOST tensors (pipelined H2D/compute/D2H)",
+        py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("dupdates"), py::arg("dmu_ext"), py::arg("dnu_ext"),
+        py::arg("out"), py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("count"),
+        py::arg("slice_elems") = 0);
+  // -- utilities
+  mod.def("kernel_launches", []() { return b200_adam_kernel_launches(); });
+  mod.def("abi_version", []() { return b200_adam_abi_version(); });
+  mod.def("set_tuning", [](int ctas_per_sm, int tiles_per_chunk) {
+    check(b200_adam_set_tuning(ctas_per_sm, tiles_per_chunk), "set_tuning");
+  }, py::arg("ctas_per_sm") = 0, py::arg("tiles_per_chunk") = 0);
+  mod.def("query_launch", [](int dtype, bool backward, int64_t n) {
+    int32_t out[5];
+    check(b200_adam_query_launch(dtype, backward ? 1 : 0, n, out), "query_launch");
+    return py::dict(py::arg("grid") = out[0], py::arg("block") = out[1], py::arg("chunk_elems") = out[2],
+                    py::arg("vector_elems") = out[3], py::arg("unroll") = out[4]);
+  }, py::arg("dtype"), py::arg("backward"), py::arg("n"));
+  mod.def("host_release", []() { b200_adam_host_release(); });
+}

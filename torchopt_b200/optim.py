@@ -1,0 +1,169 @@
+"""Thin callers of the hot path: ``adam`` / ``adamw`` recipes, ``apply_updates``, ``MetaAdam``, ``Adam``.
+
+These are the reference's *unchanged callers* ("OUT OF SCOPE -- unchanged callers"): in a real
+deployment TorchOpt's own ``torchopt.adam`` / ``torchopt.MetaAdam`` sit here and only ``torchopt._C`` +
+``torchopt/accelerated_op/adam_op.py`` are swapped.  They are restated minimally (flat lists of
+tensors only) so the BASELINE configs -- ``adam(use_accelerated_op=True)`` K-step unrolls, ``MetaAdam`` MAML inner
+loops -- can run on a box that has no TorchOpt installed.  Reference call stack: alias/adam.py:116-137,
+optim/meta/base.py:58-96, optim/base.py:99-124, update.py:69-81, transform/scale.py:86-105.
+"""
+from __future__ import annotations
+
+from typing import Any, Iterable, Sequence
+
+import torch
+from torch import nn
+
+from torchopt_b200.transform import GradientTransformation, scale_by_accelerated_adam
+
+
+def chain_flat(*transforms: GradientTransformation) -> GradientTransformation:
+    """Compose transformations over a flat list of leaves (combine.py:49-102, base.py:184-200)."""
+    transforms = tuple(t for t in transforms if t is not None)
+
+    def init_fn(params: Sequence) -> tuple:
+        return tuple(t.init(params) for t in transforms)
+
+    def update_fn(updates: Sequence, state: tuple, *, params: Any = None, inplace: bool = True):
+        new_state = []
+        for t, s in zip(transforms, state):
+            updates, s = t.update(updates, s, params=params, inplace=inplace)
+            new_state.append(s)
+        return updates, tuple(new_state)
+
+    return GradientTransformation(init_fn, update_fn)
+
+
+def scale(step_size: float) -> GradientTransformation:
+    """``g * step_size`` per leaf (transform/scale.py:86-105)."""
+
+    def update_fn(updates: Sequence, state: Any, *, params: Any = None, inplace: bool = True):  # noqa: ARG001
+        if inplace:
+            out = [None if g is None else g.mul_(step_size) for g in updates]
+        else:
+            out = [None if g is None else g.mul(step_size) for g in updates]
+        return out, state
+
+    return GradientTransformation(lambda params: (), update_fn)
+
+
+def flip_sign_and_add_weight_decay(weight_decay: float = 0.0, maximize: bool = False):
+    """``g <- (+/-)g + wd * p`` (alias/utils.py:52-191); identity (None) when there is nothing to do."""
+    if weight_decay == 0.0 and not maximize:
+        return None
+    if not weight_decay >= 0.0:
+        raise ValueError(f"Invalid weight_decay value: {weight_decay}")
+
+    def update_fn(updates: Sequence, state: Any, *, params: Any = None, inplace: bool = True):
+        if weight_decay != 0.0 and params is None:
+            raise ValueError("params are required for weight decay")
+        out = []
+        for i, g in enumerate(updates):
+            if g is None:
+                out.append(None)
+                continue
+            if maximize:
+                g = g.neg_() if inplace else g.neg()
+            if weight_decay != 0.0:
+                g = g.add_(params[i], alpha=weight_decay) if inplace else g.add(params[i], alpha=weight_decay)
+            out.append(g)
+        return out, state
+
+    return GradientTransformation(lambda params: (), update_fn)
+
+
+# pylint: disable-next=too-many-arguments
+def adam(lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, *,
+         eps_root: float = 0.0, moment_requires_grad: bool = False, maximize: bool = False,
+         use_accelerated_op: bool = True) -> GradientTransformation:
+    """Functional Adam over flat leaf lists with the accelerated op (alias/adam.py:55-137)."""
+    if not use_accelerated_op:
+        raise NotImplementedError("torchopt_b200 only provides the accelerated-op path (use_accelerated_op=True)")
+    if not (callable(lr) or lr >= 0.0):
+        raise ValueError(f"Invalid learning rate: {lr}")
+    b1, b2 = betas
+    return chain_flat(
+        flip_sign_and_add_weight_decay(weight_decay, maximize),
+        scale_by_accelerated_adam.flat(b1=b1, b2=b2, eps=eps, eps_root=eps_root,
+                                       moment_requires_grad=moment_requires_grad),
+        scale(-lr),
+    )
+
+
+def apply_updates(params: Sequence, updates: Sequence, *, inplace: bool = True) -> list:
+    """``p + u`` per leaf (update.py:39-81): in place on ``p.data`` or as a new differentiable tensor."""
+    out = []
+    for p, u in zip(params, updates):
+        if u is None:
+            out.append(p)
+        elif inplace:
+            p.data.add_(u)
+            out.append(p)
+        else:
+            out.append(p.add(u))
+    return out
+
+
+class MetaAdam:
+    """Differentiable Adam over an ``nn.Module`` (optim/meta/adam.py:33-92 + optim/meta/base.py:35-129).
+
+    ``step(loss)`` takes ``autograd.grad(loss, params, create_graph=True)``, runs the fused Adam update
+    out of place and rebinds the module's parameters to the new (non-leaf) tensors, so an outer loss can
+    back-propagate through the whole unroll.
+    """
+
+    # pylint: disable-next=too-many-arguments
+    def __init__(self, module: nn.Module, lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 0.0, *, eps_root: float = 0.0,
+                 moment_requires_grad: bool = True, maximize: bool = False, use_accelerated_op: bool = True) -> None:
+        self.impl = adam(lr, betas, eps, weight_decay, eps_root=eps_root, moment_requires_grad=moment_requires_grad,
+                         maximize=maximize, use_accelerated_op=use_accelerated_op)
+        self.module = module
+        # (owner module, attribute name) for every parameter slot, in named_parameters order
+        self.slots = [(m, name) for m in module.modules() for name, p in m._parameters.items() if p is not None]
+        self.state = None
+
+    def params(self) -> list:
+        return [m._parameters[name] for m, name in self.slots]
+
+    def step(self, loss: torch.Tensor) -> None:
+        flat = self.params()
+        if self.state is None:
+            self.state = self.impl.init(flat)
+        grads = torch.autograd.grad(loss, flat, create_graph=True, allow_unused=True)
+        updates, self.state = self.impl.update(list(grads), self.state, params=flat, inplace=False)
+        for (m, name), p in zip(self.slots, apply_updates(flat, updates, inplace=False)):
+            m._parameters[name] = p
+
+    def state_dict(self) -> Any:
+        return self.state
+
+    def load_state_dict(self, state: Any) -> None:
+        self.state = state
+
+
+class Adam:
+    """In-place (non-differentiable) Adam over an iterable of parameters (optim/adam.py + optim/base.py:99-124)."""
+
+    # pylint: disable-next=too-many-arguments
+    def __init__(self, params: Iterable[torch.Tensor], lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 0.0, *, eps_root: float = 0.0, maximize: bool = False,
+                 use_accelerated_op: bool = True) -> None:
+        self.params = list(params)
+        self.impl = adam(lr, betas, eps, weight_decay, eps_root=eps_root, maximize=maximize,
+                         use_accelerated_op=use_accelerated_op)
+        self.state = self.impl.init(self.params)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        for p in self.params:
+            if p.grad is not None:
+                if set_to_none:
+                    p.grad = None
+                else:
+                    p.grad.detach_().zero_()
+
+    @torch.no_grad()
+    def step(self) -> None:
+        grads = [p.grad for p in self.params]
+        updates, self.state = self.impl.update(grads, self.state, params=self.params, inplace=True)
+        apply_updates(self.params, updates, inplace=True)

@@ -1,0 +1,86 @@
+"""Multi-GPU plumbing for the Adam hot path (one process per GPU, ``torch.distributed``).
+
+Two cases, and only these two:
+
+* **Flat Adam state** shards naturally: element i depends only on element i of the other arrays, so rank r owns the
+  contiguous range ``shard_range(n, r, N)`` (vector-aligned split) or a bin of whole leaves
+  (``partition_leaves``) and runs the same kernels on it.  No collective exists on this path.
+* **Task-batched meta-learning** (MAML): meta-parameters are replicated, rank r runs the tasks
+  ``task_slice(num_tasks, r, N)``, the unrolled inner loops are entirely local, and the meta-gradients are summed
+  with ONE all-reduce over ONE flattened fp32 bucket (``allreduce_meta_grads``).  This replaces the reference's RPC
+  fan-out + CPU ``torch.mean(torch.stack(...))`` + dist-autograd gradient pull
+  (/root/reference/torchopt/distributed/api.py:264-271,315-322, distributed/autograd.py:79-91).
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int, align: int = 8) -> tuple[int, int]:
+    """Contiguous element range ``[lo, hi)`` of rank ``rank`` when ``n`` elements are split over ``world`` ranks.
+
+    Interior boundaries are multiples of ``align`` elements (8 fp32 = one 256-bit vector) so every shard base
+    stays vector-aligned; the ranges tile ``[0, n)`` exactly and differ in size by at most ``align``.
+    """
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    if n < 0 or align <= 0:
+        raise ValueError("n must be >= 0 and align > 0")
+    blocks = (n + align - 1) // align
+    per, extra = divmod(blocks, world)
+
+    def edge(r: int) -> int:
+        return min(n, (r * per + min(r, extra)) * align)
+
+    return edge(rank), edge(rank + 1)
+
+
+def partition_leaves(sizes: Sequence[int], world: int) -> list[list[int]]:
+    """Leaf-granular partition: greedy longest-processing-time bin packing of leaf indices over ``world`` ranks.
+    Deterministic (ties broken by index), so every rank computes the same assignment without communicating."""
+    if world <= 0:
+        raise ValueError("world must be positive")
+    bins: list[list[int]] = [[] for _ in range(world)]
+    load = [0] * world
+    for i in sorted(range(len(sizes)), key=lambda k: (-sizes[k], k)):
+        r = min(range(world), key=lambda k: (load[k], k))
+        bins[r].append(i)
+        load[r] += sizes[i]
+    for b in bins:
+        b.sort()
+    return bins
+
+
+def task_slice(num_tasks: int, rank: int, world: int) -> range:
+    """Tasks of a meta-batch owned by ``rank`` (contiguous blocks; sizes differ by at most one)."""
+    per, extra = divmod(num_tasks, world)
+    lo = rank * per + min(rank, extra)
+    return range(lo, lo + per + (1 if rank < extra else 0))
+
+
+def allreduce_meta_grads(grads: Sequence[torch.Tensor | None], *, scale: float | None = None,
+                         group: dist.ProcessGroup | None = None) -> list[torch.Tensor | None]:
+    """Sum meta-gradients over ranks with a single all-reduce of one flattened bucket, in place.
+
+    ``scale`` (e.g. ``1 / num_tasks``) is applied BEFORE the reduction, reproducing the reference's
+    ``torch.mean(torch.stack(task_losses))`` (examples/few-shot/maml_omniglot.py:175) when every rank contributes
+    the plain sum of its tasks' gradients.  ``None`` entries are treated as zeros of unknown shape and must be
+    ``None`` on every rank.  Without an initialised process group this is a local scale only (world size 1).
+    """
+    live = [g for g in grads if g is not None]
+    if not live:
+        return list(grads)
+    bucket = torch.cat([g.reshape(-1).to(torch.float32) for g in live])
+    if scale is not None:
+        bucket.mul_(scale)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in live:
+        k = g.numel()
+        g.copy_(bucket[off:off + k].view_as(g))
+        off += k
+    return list(grads)

@@ -1,0 +1,159 @@
+"""``scale_by_accelerated_adam`` -- the caller of the hot path, re-built around ONE multi-tensor launch.
+
+Mirrors /root/reference/torchopt/transform/scale_by_adam.py:225-420 (same constructor arguments, same
+``GradientTransformation(init, update)`` protocol of torchopt/base.py:118-151, same
+``ScaleByAdamState(mu, nu, count)`` state with ``count`` a per-leaf 0-dim int64 tensor on the leaf's device),
+but ``update`` hands every leaf to ``AdamOp.multi`` at once instead of looping ``op(mu, nu, g, count)`` in Python,
+and the step counters carry a host mirror:
+
+* reference, per leaf per step: ``count + (count != INT64_MAX)`` = 3 tiny kernels (transform/utils.py:117-121)
+  plus a device->host sync when pybind converts the count tensor to ``size_t``;
+* here, per step: one small host->device copy builds all new counters; the kernels get their bias corrections
+  from the host mirror (``tensor._b200_host_count``), so nothing synchronises.  A state whose counters lack the
+  mirror (e.g. one deserialised by the user) is read once with ``int()`` and tagged.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, NamedTuple, Sequence
+
+import torch
+
+from torchopt_b200 import _pytree
+from torchopt_b200.accelerated_op.adam_op import INT64_MAX, AdamOp, count_as_int
+
+
+# A/B switch for parity tests: False routes the differentiable path through the reference's three-node graph
+# (MuOp/NuOp/UpdatesOp, three launches per leaf) instead of the fused single node.
+FUSED_GRAPH = True
+
+
+class GradientTransformation(NamedTuple):
+    """``(init, update)`` pair -- torchopt/base.py:118-151."""
+
+    init: Callable
+    update: Callable
+
+
+class ScaleByAdamState(NamedTuple):
+    """State for the Adam algorithm -- transform/scale_by_adam.py:58-63."""
+
+    mu: Any
+    nu: Any
+    count: Any
+
+
+def _tag(count: torch.Tensor, host: int) -> torch.Tensor:
+    count._b200_host_count = host  # type: ignore[attr-defined]
+    return count
+
+
+def make_counts(values: Sequence[int | None], devices: Sequence[torch.device | None]) -> list:
+    """0-dim int64 device tensors holding ``values`` (one host->device copy per device), each tagged with its
+    host mirror.  ``None`` entries stay ``None``."""
+    out: list = [None] * len(values)
+    by_dev: dict = {}
+    for i, (v, d) in enumerate(zip(values, devices)):
+        if v is not None:
+            by_dev.setdefault(d, []).append(i)
+    for dev, idx in by_dev.items():
+        host = torch.tensor([values[i] for i in idx], dtype=torch.int64)
+        if dev.type == "cuda":
+            host = host.pin_memory() if torch.cuda.is_available() else host
+            vec = host.to(dev, non_blocking=True)
+        else:
+            vec = host.to(dev)
+        for j, i in enumerate(idx):
+            out[i] = _tag(vec[j], values[i])
+    return out
+
+
+def inc_count_flat(updates: Sequence, counts: Sequence) -> list:
+    """``count + 1`` (saturating at INT64_MAX) for leaves that received an update; others pass through.
+    Same values as transform/utils.py:111-122, built from the host mirrors."""
+    values, devices = [], []
+    for g, c in zip(updates, counts):
+        if g is None or c is None:
+            values.append(None), devices.append(None)
+            continue
+        host = count_as_int(c)
+        if getattr(c, "_b200_host_count", None) is None and isinstance(c, torch.Tensor):
+            _tag(c, host)
+        values.append(host + (host != INT64_MAX))
+        devices.append(c.device if isinstance(c, torch.Tensor) else torch.device("cpu"))
+    fresh = make_counts(values, devices)
+    return [fresh[i] if values[i] is not None else counts[i] for i in range(len(counts))]
+
+
+# pylint: disable-next=too-many-arguments
+def _scale_by_accelerated_adam(b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, eps_root: float = 0.0,
+                               moment_requires_grad: bool = False, *,
+                               already_flattened: bool = False) -> GradientTransformation:
+    # argument validation as in transform/scale_by_adam.py:292-299
+    if not eps >= 0.0:
+        raise ValueError(f"Invalid epsilon value: {eps}")
+    if not 0.0 <= b1 < 1.0:
+        raise ValueError(f"Invalid beta parameter at index 0: {b1}")
+    if not 0.0 <= b2 < 1.0:
+        raise ValueError(f"Invalid beta parameter at index 1: {b2}")
+
+    def init_flat(params: Sequence) -> ScaleByAdamState:
+        leaves = list(params)
+        count = make_counts([None if p is None else 0 for p in leaves],
+                            [None if p is None else p.device for p in leaves])
+        mu = [None if p is None else torch.zeros_like(p, requires_grad=moment_requires_grad) for p in leaves]
+        nu = [None if p is None else torch.zeros_like(p, requires_grad=moment_requires_grad) for p in leaves]
+        return ScaleByAdamState(mu=mu, nu=nu, count=count)
+
+    def update_flat(updates: Sequence, state: ScaleByAdamState, inplace: bool):
+        op = AdamOp(b1=b1, b2=b2, eps=eps, eps_root=eps_root, inplace=inplace, fused=FUSED_GRAPH)
+        count_inc = inc_count_flat(updates, state.count)
+        new_mu, new_nu, new_updates = op.multi(state.mu, state.nu, updates, count_inc)
+        return new_updates, new_mu, new_nu, count_inc
+
+    def rewrap(new: list, like: Any) -> Any:  # keep the container type of the caller (list / tuple)
+        return new if isinstance(like, list) else type(like)(new) if isinstance(like, tuple) else new
+
+    if already_flattened:
+
+        def init_fn(params: Sequence) -> ScaleByAdamState:
+            st = init_flat(params)
+            return ScaleByAdamState(*(rewrap(x, params) for x in st))
+
+        def update_fn(updates: Sequence, state: ScaleByAdamState, *, params: Any = None,  # noqa: ARG001
+                      inplace: bool = True):
+            new_updates, new_mu, new_nu, count_inc = update_flat(updates, state, inplace)
+            return rewrap(new_updates, updates), ScaleByAdamState(
+                mu=rewrap(new_mu, state.mu), nu=rewrap(new_nu, state.nu), count=rewrap(count_inc, state.count))
+
+    else:
+
+        def init_fn(params: Any) -> ScaleByAdamState:
+            leaves, spec = _pytree.tree_flatten(params)
+            st = init_flat(leaves)
+            return ScaleByAdamState(*(_pytree.tree_unflatten(spec, x) for x in st))
+
+        def update_fn(updates: Any, state: ScaleByAdamState, *, params: Any = None,  # noqa: ARG001
+                      inplace: bool = True):
+            leaves, spec = _pytree.tree_flatten(updates)
+            flat_state = ScaleByAdamState(*(_pytree.tree_flatten(x)[0] for x in state))
+            new_updates, new_mu, new_nu, count_inc = update_flat(leaves, flat_state, inplace)
+            un = _pytree.tree_unflatten
+            return un(spec, new_updates), ScaleByAdamState(mu=un(spec, new_mu), nu=un(spec, new_nu),
+                                                           count=un(spec, count_inc))
+
+    return GradientTransformation(init_fn, update_fn)
+
+
+def scale_by_accelerated_adam(b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, eps_root: float = 0.0,
+                              moment_requires_grad: bool = False) -> GradientTransformation:
+    """Rescale updates according to the Adam algorithm with the B200 fused operator (pytree variant)."""
+    return _scale_by_accelerated_adam(b1, b2, eps, eps_root, moment_requires_grad, already_flattened=False)
+
+
+def _flat(b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, eps_root: float = 0.0,
+          moment_requires_grad: bool = False) -> GradientTransformation:
+    return _scale_by_accelerated_adam(b1, b2, eps, eps_root, moment_requires_grad, already_flattened=True)
+
+
+scale_by_accelerated_adam.flat = _flat  # type: ignore[attr-defined]
+scale_by_accelerated_adam.impl = _scale_by_accelerated_adam  # type: ignore[attr-defined]
