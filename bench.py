@@ -123,6 +123,14 @@ def ncu_traffic() -> dict | None:
         return None
 
 
+def _scaled_traffic(traffic: dict | None, which: str, n: int):
+    """Measured DRAM bytes per launch for an n-element launch: ncu's per-element figure x n (the capture is taken at
+    a smaller n so that ncu's kernel replay stays cheap; bytes/elem is size-independent for these streams)."""
+    if not traffic or f"{which}_dram_bytes_per_elem" not in traffic:
+        return None
+    return traffic[f"{which}_dram_bytes_per_elem"] * n
+
+
 # ---------------------------------------------------------------------------------------------------------
 # the reference's CPU adam_op (oracle/_ref) -- one differentiable fwd+bwd exactly as autograd would run it
 # ---------------------------------------------------------------------------------------------------------
@@ -410,11 +418,13 @@ def run_b200(args) -> None:
         "roofline": {"bound": "hbm", "kernel": "fused_backward (stream_kernel<BwdH<f32,BWD_FULL>>)",
                      "achieved": ach_bwd, "peak": peak, "unit": "GB/s", "frac": ach_bwd / peak,
                      "peak_source": peak_src, "frac_of_nominal_8TBs": ach_bwd / 8000.0,
-                     "traffic": (traffic or {}).get("backward_dram_bytes_per_launch"),
+                     "traffic": _scaled_traffic(traffic, "backward", n),
+                     "traffic_source": (f"ncu --set full at n={traffic['n_elems']} scaled by n/n_ncu "
+                                        f"({traffic['source']})" if traffic else None),
                      "algorithmic_bytes_per_launch": BYTES_BWD * n, "avg_launch_ms": bwd_avg_ms,
                      "forward": {"achieved": ach_fwd, "frac": ach_fwd / peak, "avg_launch_ms": fwd_avg_ms,
                                  "algorithmic_bytes_per_launch": BYTES_FWD * n,
-                                 "traffic": (traffic or {}).get("forward_dram_bytes_per_launch")},
+                                 "traffic": _scaled_traffic(traffic, "forward", n)},
                      "step_hbm_gbs_per_gpu": step_gbs, "step_frac": step_gbs / peak},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "cpu_baseline": cpu_baseline,
     }

@@ -150,8 +150,9 @@ const char *b200_adam_error_string(int code);
 /* Number of CUDA kernels this library has launched in this process so far (for bench.py's gpu_launches). */
 uint64_t b200_adam_kernel_launches(void);
 
-/* Launch tuning: resident CTAs per SM of the persistent grid (0 = library default) and the number of
- * block-tiles per chunk (0 = default).  Process-wide; intended for the bench/tuning harness. */
+/* Launch tuning.  ctas_per_sm: 0 = default, one CTA per chunk (non-persistent grid); k > 0 = persistent grid of
+ * k CTAs per SM walking the chunks in grid-stride order.  tiles_per_chunk: block-tiles per chunk (0 = default, 1).
+ * Process-wide; intended for the bench/tuning harness. */
 int b200_adam_set_tuning(int ctas_per_sm, int tiles_per_chunk);
 
 /* Writes the launch geometry the library would use for an `n`-element single-leaf fused launch:

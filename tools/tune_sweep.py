@@ -22,21 +22,30 @@ from concurrent.futures import ThreadPoolExecutor
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT_DIR = os.path.join(ROOT, "build", "tune")
-VARIANTS = [(p, u, b) for p, u in ((4, 1), (4, 2), (4, 4), (8, 1), (8, 2), (8, 4)) for b in (128, 256, 512)]
+L2_POLICIES = {"none": ("", ""), "ldEF": (".L2::evict_first", ""), "stEF": ("", ".L2::evict_first"),
+               "ldstEF": (".L2::evict_first", ".L2::evict_first")}
+if os.environ.get("TUNE_ROUND", "2") == "1":   # round-1 sweep: vector width / unroll / CTA size
+    VARIANTS = [(p, u, b, "none") for p, u in ((4, 1), (4, 2), (4, 4), (8, 1), (8, 2), (8, 4)) for b in (128, 256, 512)]
+    RUNTIME = [(c, t) for c in (0, 1, 2, 4, 8, 16) for t in (1, 2, 4, 8)]
+else:                                         # round-2 sweep: L2 eviction priority on the best shapes
+    VARIANTS = [(8, u, b, pol) for u in (1, 2) for b in (256, 512, 1024) for pol in L2_POLICIES]
+    RUNTIME = [(0, 1), (0, 2), (16, 2), (32, 2)]
 
 
-def lib_path(p, u, b):
-    return os.path.join(OUT_DIR, f"libb200adam_P{p}U{u}B{b}.so")
+def lib_path(p, u, b, pol="none"):
+    return os.path.join(OUT_DIR, f"libb200adam_P{p}U{u}B{b}_{pol}.so")
 
 
 def build_one(v):
-    p, u, b = v
+    p, u, b, pol = v
+    ld, st = L2_POLICIES[pol]
     csrc = os.path.join(ROOT, "torchopt_b200", "csrc")
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--fmad=false",
            "-Xcompiler", "-fPIC", "-shared", "-DB200_ADAM_TUNE_F32_ONLY", f"-DB200_ADAM_BLOCK={b}",
            f"-DB200_P_FWD={p}", f"-DB200_U_FWD={u}", f"-DB200_P_BWD={p}", f"-DB200_U_BWD={u}",
+           f'-DB200_LD_L2="{ld}"', f'-DB200_ST_L2="{st}"',
            f"-I{os.path.join(ROOT, 'include')}", f"-I{csrc}", os.path.join(csrc, "b200_adam.cu"),
-           os.path.join(csrc, "host_pipeline.cu"), "-o", lib_path(p, u, b)]
+           os.path.join(csrc, "host_pipeline.cu"), "-o", lib_path(p, u, b, pol)]
     subprocess.check_call(cmd)
     return v
 
@@ -62,8 +71,8 @@ def run(n_log2: int, out_path: str):
     mu2, nu2, u, dg, dmu, dnu = (x.data_ptr() for x in o)
     stream = torch.cuda.current_stream().cuda_stream
     results = []
-    for (p, uu, b) in VARIANTS:
-        path = lib_path(p, uu, b)
+    for (p, uu, b, pol) in VARIANTS:
+        path = lib_path(p, uu, b, pol)
         if not os.path.isfile(path):
             continue
         lib = abi.load(path)
@@ -73,19 +82,19 @@ def run(n_log2: int, out_path: str):
         prep.fwd = [abi._ptrs([x]) for x in (g, mu, nu, mu2, nu2, u)]
         prep.bwd = [abi._ptrs([x]) for x in (du, u, mu2, g, dme, dne, dg, dmu, dnu)]
         prep.h = (0.9, 0.999, 1e-8, 1e-8)
-        for ctas, tiles in itertools.product((0, 1, 2, 4, 8, 16, 1 << 20), (1, 2, 4, 8)):
+        for ctas, tiles in RUNTIME:
             assert lib.b200_adam_set_tuning(ctas, tiles) == 0
-            row = {"P": p, "U": uu, "block": b, "ctas_per_sm": ctas, "tiles_per_chunk": tiles}
+            row = {"P": p, "U": uu, "block": b, "l2": pol, "ctas_per_sm": ctas, "tiles_per_chunk": tiles}
             for name, fn, nbytes in (("fwd", prep.forward, 24 * n), ("bwd", prep.backward, 36 * n)):
                 for _ in range(3):
                     assert fn(stream) == 0
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                for _ in range(10):
+                for _ in range(20):
                     fn(stream)
                 e1.record()
                 torch.cuda.synchronize()
-                ms = e0.elapsed_time(e1) / 10
+                ms = e0.elapsed_time(e1) / 20
                 row[f"{name}_ms"] = ms
                 row[f"{name}_gbs"] = nbytes / (ms * 1e-3) / 1e9
             results.append(row)

@@ -6,8 +6,11 @@
 //   * 128-bit or 256-bit (LDG.E.256 / STG.E.256, new on sm_100) vector accesses, fully coalesced: lane k of a
 //     warp touches vector k of a 32-vector run; the read-only streams use ld.global.nc + L1::no_allocate;
 //   * U independent vector loads per array are issued front-batched before any use (MLP = U x arrays);
-//   * persistent CTAs walk "chunks" (a chunk = a few block-tiles of ONE leaf) in grid-stride order, so the
-//     CTAs resident at any instant cover one contiguous window of every array;
+//   * the work unit is a "chunk" (one or a few block-tiles of ONE leaf); CTAs walk chunks in grid-stride order, so
+//     the CTAs resident at any instant cover one contiguous window of every array.  By default the grid has one
+//     CTA per chunk (measured best on B200: the hardware CTA scheduler back-fills SMs and de-phases the load and
+//     store bursts of neighbouring CTAs, +6-9% over a lock-step persistent grid); a persistent grid of k CTAs per
+//     SM is a run-time option (b200_adam_set_tuning);
 //   * multi-tensor: the leaf table (pointers, sizes, per-leaf bias corrections, chunk prefix sums) rides in
 //     the kernel parameters (__grid_constant__, up to 32 KB on sm_100) -- no device-side table, no extra copy,
 //     graph-capturable; a single flat tensor is simply the 1-leaf table.
@@ -90,6 +93,14 @@ struct Down<bf16_t, float> {
 // ------------------------------------------------------------------------------------------------
 // vector global-memory access: BYTES in {8, 16, 32}; NC = read-only (non-coherent) path allowed
 // ------------------------------------------------------------------------------------------------
+// L2 eviction priority of the streams (every byte is touched exactly once per launch); overridable for sweeps.
+#ifndef B200_LD_L2
+#define B200_LD_L2 ""
+#endif
+#ifndef B200_ST_L2
+#define B200_ST_L2 ""
+#endif
+
 template <int BYTES, bool NC>
 struct VecIO;
 
@@ -97,7 +108,7 @@ template <bool NC>
 struct VecIO<32, NC> {
   static __device__ __forceinline__ void ld(uint32_t (&w)[8], const void *p) {
     if (NC)
-      asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      asm volatile("ld.global.nc.L1::no_allocate" B200_LD_L2 ".v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                    : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                    : "l"(p));
     else
@@ -107,7 +118,7 @@ struct VecIO<32, NC> {
                    : "memory");
   }
   static __device__ __forceinline__ void st(void *p, const uint32_t (&w)[8]) {
-    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]),
+    asm volatile("st.global.L1::no_allocate" B200_ST_L2 ".v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]),
                  "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                  : "memory");
   }
@@ -117,7 +128,7 @@ template <bool NC>
 struct VecIO<16, NC> {
   static __device__ __forceinline__ void ld(uint32_t (&w)[4], const void *p) {
     if (NC)
-      asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+      asm volatile("ld.global.nc.L1::no_allocate" B200_LD_L2 ".v4.b32 {%0,%1,%2,%3}, [%4];"
                    : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
                    : "l"(p));
     else
@@ -127,7 +138,7 @@ struct VecIO<16, NC> {
                    : "memory");
   }
   static __device__ __forceinline__ void st(void *p, const uint32_t (&w)[4]) {
-    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(w[0]), "r"(w[1]),
+    asm volatile("st.global.L1::no_allocate" B200_ST_L2 ".v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(w[0]), "r"(w[1]),
                  "r"(w[2]), "r"(w[3])
                  : "memory");
   }
@@ -137,7 +148,7 @@ template <bool NC>
 struct VecIO<8, NC> {
   static __device__ __forceinline__ void ld(uint32_t (&w)[2], const void *p) {
     if (NC)
-      asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p));
+      asm volatile("ld.global.nc.L1::no_allocate" B200_LD_L2 ".v2.b32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p));
     else
       asm volatile("ld.global.L1::no_allocate.v2.b32 {%0,%1}, [%2];"
                    : "=r"(w[0]), "=r"(w[1])
@@ -145,7 +156,7 @@ struct VecIO<8, NC> {
                    : "memory");
   }
   static __device__ __forceinline__ void st(void *p, const uint32_t (&w)[2]) {
-    asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(w[0]), "r"(w[1]) : "memory");
+    asm volatile("st.global.L1::no_allocate" B200_ST_L2 ".v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(w[0]), "r"(w[1]) : "memory");
   }
 };
 

@@ -19,7 +19,7 @@ namespace b200adam {
 // ---- launch configuration (chosen from the on-device sweep recorded in profiles/) ------------------
 // vector width P (elements), unroll U (vectors in flight per array per thread), CTA size.
 #ifndef B200_ADAM_BLOCK
-#define B200_ADAM_BLOCK 256
+#define B200_ADAM_BLOCK 512
 #endif
 template <typename TG, typename TS>
 struct Cfg;  // fwd / bwd / unfused vector configs per dtype family
@@ -28,13 +28,13 @@ struct Cfg;  // fwd / bwd / unfused vector configs per dtype family
 #define B200_P_FWD 8
 #endif
 #ifndef B200_U_FWD
-#define B200_U_FWD 2
+#define B200_U_FWD 1
 #endif
 #ifndef B200_P_BWD
 #define B200_P_BWD 8
 #endif
 #ifndef B200_U_BWD
-#define B200_U_BWD 1
+#define B200_U_BWD 2
 #endif
 template <>
 struct Cfg<float, float> {
@@ -103,7 +103,7 @@ template <class Op, int P, int U, int BLOCK>
 static int pick_chunk_elems(long long total_elems, int sms) {
   constexpr int TILE = BLOCK * P * U;
   int tiles = g_tiles_per_chunk.load(std::memory_order_relaxed);
-  if (tiles <= 0) tiles = 2;
+  if (tiles <= 0) tiles = 1;  // measured best (profiles/r01_tune_sweep.md): one block-tile per chunk
   // small problems: one tile per chunk so the work spreads over as many SMs as possible
   if (total_elems < (long long)TILE * tiles * sms * 4) tiles = 1;
   return TILE * tiles;
@@ -112,10 +112,10 @@ static int pick_chunk_elems(long long total_elems, int sms) {
 template <class Op, int P, int U, int BLOCK, int MAXL>
 static int launch_table(Table<Op, MAXL> &tab, const DeviceInfo &di, cudaStream_t stream) {
   if (tab.total_chunks <= 0) return 0;
-  int per_sm = g_ctas_per_sm.load(std::memory_order_relaxed);
-  if (per_sm <= 0) per_sm = occupancy_ctas_per_sm<Op, P, U, BLOCK, MAXL>();
-  long long grid = (long long)di.sms * per_sm;
-  if (grid > tab.total_chunks) grid = tab.total_chunks;
+  // default: one CTA per chunk (non-persistent).  ctas_per_sm > 0 selects a persistent grid of that many CTAs/SM.
+  const int per_sm = g_ctas_per_sm.load(std::memory_order_relaxed);
+  long long grid = tab.total_chunks;
+  if (per_sm > 0 && (long long)di.sms * per_sm < grid) grid = (long long)di.sms * per_sm;
   stream_kernel<Op, P, U, BLOCK, MAXL><<<(unsigned)grid, BLOCK, 0, stream>>>(tab);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
@@ -296,7 +296,12 @@ static int fused_backward_mode(int64_t L, const void *const *du, const void *con
     return true;
   };
   using C = Cfg<TG, TS>;
-  return run_op<Op, C::P_BWD, C::U_BWD>(L, total, 0, gs, next, stream);
+  if constexpr (MODE == BWD_GENERIC) {
+    // run-time presence flags cost registers: use half-width vectors, no unroll (stays spill-free at 512 threads)
+    return run_op<Op, C::P_BWD / 2, 1>(L, total, 0, gs, next, stream);
+  } else {
+    return run_op<Op, C::P_BWD, C::U_BWD>(L, total, 0, gs, next, stream);
+  }
 }
 
 template <typename TG, typename TS, typename CT>
@@ -432,11 +437,11 @@ int b200_adam_query_launch(int dtype, int backward, int64_t n, int32_t out[5]) {
     default: return B200_ADAM_E_DTYPE;
   }
 #undef B200_Q
-  int per_sm = g_ctas_per_sm.load();
-  if (per_sm <= 0) per_sm = occ;
-  long long chunks = (n + chunk - 1) / chunk;
-  long long grid = (long long)di.sms * per_sm;
-  if (grid > chunks) grid = chunks;
+  const int per_sm = g_ctas_per_sm.load();
+  const long long chunks = (n + chunk - 1) / chunk;
+  long long grid = chunks;
+  if (per_sm > 0 && (long long)di.sms * per_sm < grid) grid = (long long)di.sms * per_sm;
+  (void)occ;
   out[0] = (int32_t)grid, out[1] = BLOCK, out[2] = chunk, out[3] = P, out[4] = U;
   return 0;
 }
