@@ -1,0 +1,165 @@
+"""CPU tests of the host-side logic: shard/partition math, the pytree shim, step-counter mirroring, and the
+N > 1 paths under gloo with world_size 2 (flat shards tile the state exactly; the task-parallel meta-gradient
+all-reduce equals the single-process mean)."""
+from __future__ import annotations
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import assert_bits_equal
+
+
+def test_shard_range_tiles_and_aligns():
+    from torchopt_b200.parallel import shard_range
+    for n in (0, 1, 7, 8, 9, 1000, 2 ** 20 + 3, 2 ** 30):
+        for world in (1, 2, 3, 4, 8):
+            edges = [shard_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for (lo, hi), (lo2, _) in zip(edges, edges[1:]):
+                assert hi == lo2 and lo <= hi
+            for lo, hi in edges[:-1]:
+                assert hi % 8 == 0 or hi == n
+            sizes = [hi - lo for lo, hi in edges]
+            if n >= 8 * world:
+                assert max(sizes) - min(sizes) < 16
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def test_partition_leaves_and_task_slice():
+    from torchopt_b200.parallel import partition_leaves, task_slice
+    sizes = [9408, 64, 64, 36864, 64, 64, 2359296, 512, 512, 512000, 1000]
+    for world in (1, 2, 4, 8):
+        bins = partition_leaves(sizes, world)
+        assert sorted(i for b in bins for i in b) == list(range(len(sizes)))
+        loads = [sum(sizes[i] for i in b) for b in bins]
+        assert max(loads) <= max(max(sizes), sum(sizes) / world * 1.34 + max(sizes) * (world == 1))
+    assert partition_leaves(sizes, 3) == partition_leaves(sizes, 3)  # deterministic
+    for num, world in ((32, 8), (32, 3), (5, 8), (0, 2)):
+        got = [list(task_slice(num, r, world)) for r in range(world)]
+        assert sum(got, []) == list(range(num))
+        assert max(map(len, got)) - min(map(len, got)) <= 1
+
+
+def test_pytree_shim_none_is_leaf():
+    from collections import namedtuple
+    from torchopt_b200 import _pytree
+    NT = namedtuple("NT", ["a", "b"])
+    tree = {"z": [1, None, (2, 3)], "a": NT(4, {"k": 5}), "m": ()}
+    leaves, spec = _pytree.tree_flatten(tree)
+    assert leaves == [4, 5, 1, None, 2, 3]          # dict keys sorted; None is a leaf
+    assert spec.num_leaves == 6
+    back = _pytree.tree_unflatten(spec, leaves)
+    assert back == tree and isinstance(back["a"], NT)
+    doubled = _pytree.tree_map(lambda x, y: None if x is None else x + y, tree, tree)
+    assert doubled["z"] == [2, None, (4, 6)] and doubled["a"].b["k"] == 10
+    with pytest.raises(ValueError):
+        _pytree.tree_map(lambda x, y: x, tree, {"z": 1})
+
+
+def test_step_counters_host_mirror_cpu():
+    """inc_count semantics of transform/utils.py:111-122 with the host mirror: +1 where a gradient exists,
+    saturating at INT64_MAX, untouched where the gradient is None; counters stay 0-dim int64 tensors."""
+    from torchopt_b200.accelerated_op.adam_op import INT64_MAX, count_as_int
+    from torchopt_b200.transform import inc_count_flat, make_counts
+    dev = torch.device("cpu")
+    counts = make_counts([0, 5, None, INT64_MAX], [dev, dev, None, dev])
+    assert counts[2] is None and all(c.dim() == 0 and c.dtype == torch.int64 for c in counts if c is not None)
+    g = [torch.ones(1), None, None, torch.ones(1)]
+    new = inc_count_flat(g, counts)
+    assert [None if c is None else int(c) for c in new] == [1, 5, None, INT64_MAX]
+    assert new[1] is counts[1]
+    assert count_as_int(new[0]) == 1 and new[0]._b200_host_count == 1
+    bare = [torch.tensor(41), torch.tensor(7)]       # user-built counters without a mirror
+    new = inc_count_flat([torch.ones(1), torch.ones(1)], bare)
+    assert [int(c) for c in new] == [42, 8] and count_as_int(3) == 3
+
+
+def test_transform_validation_and_none_leaves_cpu():
+    import torchopt_b200 as tb
+    with pytest.raises(ValueError):
+        tb.scale_by_accelerated_adam(b1=1.0)
+    with pytest.raises(ValueError):
+        tb.scale_by_accelerated_adam(eps=-1.0)
+    with pytest.raises(NotImplementedError):
+        tb.adam(use_accelerated_op=False)
+    # empty / None-only pytrees never reach a kernel (reference tests/test_alias.py:35-79)
+    tx = tb.scale_by_accelerated_adam()
+    for params in ((), [], {}, {"a": None}, (None, None)):
+        state = tx.init(params)
+        updates, state = tx.update(params, state, inplace=False)
+        assert updates == params
+    opt = tb.adam(1e-3)
+    st = opt.init([])
+    assert opt.update([], st, params=[], inplace=True)[0] == []
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# world_size-2 gloo
+# ---------------------------------------------------------------------------------------------------------------
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, tmp: str):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import adam_oracle as ao
+        from torchopt_b200.parallel import allreduce_meta_grads, shard_range, task_slice
+        # (1) flat-state sharding: every rank processes its contiguous range with the same (oracle) arithmetic;
+        #     the concatenation must equal the unsharded result bit-for-bit, with no communication in the op.
+        n = 100_003
+        rng = np.random.default_rng(7)
+        g = (rng.standard_normal(n) * 1e-2).astype(np.float32)
+        mu = (rng.standard_normal(n) * 1e-2).astype(np.float32)
+        nu = (rng.random(n) * 1e-4).astype(np.float32)
+        lo, hi = shard_range(n, rank, world)
+        orc = ao.COracle()
+        _, _, u = ao.fused_forward(orc, g[lo:hi], mu[lo:hi], nu[lo:hi], 0.9, 0.999, 1e-8, 0.0, 2)
+        np.save(os.path.join(tmp, f"u_{rank}.npy"), u)
+        # (2) task-parallel meta-gradient: rank-local SUM of per-task grads, one all-reduce of one bucket,
+        #     pre-scaled by 1/num_tasks == mean over the whole meta-batch.
+        num_tasks = 7
+        torch.manual_seed(0)
+        per_task = [[torch.randn(5, 3), torch.randn(11)] for _ in range(num_tasks)]   # same on every rank
+        local = [sum(per_task[t][k] for t in task_slice(num_tasks, rank, world)) for k in range(2)]
+        local.append(None)                                                            # an unused parameter
+        out = allreduce_meta_grads(local, scale=1.0 / num_tasks)
+        want = [torch.stack([per_task[t][k] for t in range(num_tasks)]).mean(0) for k in range(2)]
+        assert out[2] is None
+        for a, b in zip(out[:2], want):
+            torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-6)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    from oracle import adam_oracle as ao
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    n = 100_003
+    rng = np.random.default_rng(7)
+    g = (rng.standard_normal(n) * 1e-2).astype(np.float32)
+    mu = (rng.standard_normal(n) * 1e-2).astype(np.float32)
+    nu = (rng.random(n) * 1e-4).astype(np.float32)
+    _, _, want = ao.fused_forward(ao.COracle(), g, mu, nu, 0.9, 0.999, 1e-8, 0.0, 2)
+    got = np.concatenate([np.load(tmp_path / f"u_{r}.npy") for r in range(world)])
+    assert_bits_equal(got, want, "sharded == unsharded")
+
+
+def test_allreduce_meta_grads_single_process():
+    from torchopt_b200.parallel import allreduce_meta_grads
+    g = [torch.ones(3), None, torch.full((2, 2), 4.0)]
+    out = allreduce_meta_grads(g, scale=0.5)
+    assert out[1] is None and torch.equal(out[0], torch.full((3,), 0.5)) and torch.equal(out[2], torch.full((2, 2), 2.0))
+    assert allreduce_meta_grads([None]) == [None]

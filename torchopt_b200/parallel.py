@@ -23,7 +23,7 @@ def shard_range(n: int, rank: int, world: int, align: int = 8) -> tuple[int, int
     """Contiguous element range ``[lo, hi)`` of rank ``rank`` when ``n`` elements are split over ``world`` ranks.
 
     Interior boundaries are multiples of ``align`` elements (8 fp32 = one 256-bit vector) so every shard base
-    stays vector-aligned; the ranges tile ``[0, n)`` exactly and differ in size by at most ``align``.
+    stays vector-aligned; the ranges tile ``[0, n)`` exactly and differ in size by less than ``2 * align``.
     """
     if world <= 0 or not 0 <= rank < world:
         raise ValueError(f"bad rank/world: {rank}/{world}")
