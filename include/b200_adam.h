@@ -125,6 +125,32 @@ int b200_adam_fused_backward(int dtype, int64_t num_leaves, const void *const *d
                              const int64_t *n, const uint64_t *count, double b1, double b2, double eps_root,
                              void *stream);
 
+/* ---- whole optimizer step: Adam update + scale(step_size) + apply_updates in one launch (F32 / F64) ---------
+ * Replaces, for all leaves at once, the chain  scale_by_accelerated_adam -> scale(-lr) -> apply_updates
+ * (alias/adam.py:116-137, transform/scale.py:86-105 `g.mul(step_size)`, update.py:78-79 `p.add(u)`):
+ *   mu', nu', u as b200_adam_fused_forward ;  us = u * step_size ;  p_out = p + us      (step_size = -lr)
+ * u itself is never stored (the backward recomputes it bit-identically from mu', nu'); `us_out` may be NULL, or its
+ * entries NULL, when the caller does not need the scaled update tensor.  28 B/element fp32 (32 with us_out). */
+int b200_adam_step_forward(int dtype, int64_t num_leaves, const void *const *p, const void *const *g,
+                           const void *const *mu, const void *const *nu, void *const *p_out, void *const *mu_out,
+                           void *const *nu_out, void *const *us_out, const int64_t *n, const uint64_t *count,
+                           double b1, double b2, double eps, double eps_root, double step_size, void *stream);
+
+/* In-place, non-differentiable variant (Optimizer.step, optim/base.py:99-124): p += us, g <- us, mu <- mu', nu <- nu'. */
+int b200_adam_step_inplace(int dtype, int64_t num_leaves, void *const *p, void *const *g, void *const *mu,
+                           void *const *nu, const int64_t *n, const uint64_t *count, double b1, double b2, double eps,
+                           double eps_root, double step_size, void *stream);
+
+/* Backward of b200_adam_step_forward.  Incoming per leaf (each may be NULL): dp = gradient of p_out, dus = gradient of
+ * us_out (the array argument itself may be NULL), dmu_ext / dnu_ext = gradients of mu_out / nu_out.
+ *   du = (dp + dus) * step_size ; then exactly b200_adam_fused_backward with u recomputed from new_mu, new_nu.
+ * The gradient w.r.t. p is dp itself (p_out = p + us) and is not written by this call.  36 B/element fp32. */
+int b200_adam_step_backward(int dtype, int64_t num_leaves, const void *const *dp, const void *const *dus,
+                            const void *const *new_mu, const void *const *new_nu, const void *const *g,
+                            const void *const *dmu_ext, const void *const *dnu_ext, void *const *dg, void *const *dmu,
+                            void *const *dnu, const int64_t *n, const uint64_t *count, double b1, double b2,
+                            double eps, double eps_root, double step_size, void *stream);
+
 /* ---- host-buffer entry point (what an application holding HOST arrays calls; used for the e2e number) */
 
 /* One fused differentiable forward + backward over HOST arrays of n elements (dtype F32 only):

@@ -233,6 +233,32 @@ def fused_backward(o, du, u, new_mu, g, dmu_ext, dnu_ext, b1, b2, eps_root, coun
     return (dg if dg is not None else zeros), dmu, dnu
 
 
+def fused_step_forward(o, p, g, mu, nu, b1, b2, eps, eps_root, count, step_size):
+    """(new_p, new_mu, new_nu, us): the chain scale_by_accelerated_adam -> scale(step_size) -> apply_updates.
+    ``g.mul(step_size)`` (transform/scale.py:103) and ``p.add(u)`` (update.py:79) are single rounded ops in the
+    tensor dtype with the Python scalar rounded to that dtype once."""
+    T = p.dtype.type
+    new_mu, new_nu, u = fused_forward(o, g, mu, nu, b1, b2, eps, eps_root, count)
+    with np.errstate(all="ignore"):
+        us = u * T(step_size)
+        new_p = p + us
+    return new_p, new_mu, new_nu, us
+
+
+def fused_step_backward(o, dp, new_mu, new_nu, g, dmu_ext, dnu_ext, b1, b2, eps, eps_root, count, step_size,
+                        dus=None):
+    """(dg, dmu, dnu) for the chain above: AddBackward hands dp to the scaled update (plus ``dus`` if the scaled
+    update is used elsewhere), MulBackward multiplies by the rounded scalar, then the Adam backward."""
+    T = g.dtype.type
+    u = o.forward_updates(new_mu, new_nu, b1, b2, eps, eps_root, count)
+    du = None
+    if dp is not None or dus is not None:
+        tot = dp if dus is None else (dus if dp is None else dp + dus)
+        with np.errstate(all="ignore"):
+            du = tot * T(step_size)
+    return fused_backward(o, du, u, new_mu, g, dmu_ext, dnu_ext, b1, b2, eps_root, count)
+
+
 def load_ref():
     """Import the reference's compiled adam_op (oracle/_ref/_C.so) -> module with .adam_op; None if absent."""
     if not os.path.isfile(REF_SO):

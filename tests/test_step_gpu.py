@@ -1,0 +1,173 @@
+"""GPU parity of the whole-step kernels (Adam + scale(-lr) + apply_updates in one launch):
+through the C ABI vs the oracle composition, and through MetaAdam / Adam vs the chained path run with torch ops."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+B1, B2, EPS = 0.9, 0.999, 1e-8
+NP = {"f32": np.float32, "f64": np.float64}
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.cpu().numpy()
+
+
+def inputs(n, dt, seed):
+    rng = np.random.default_rng(seed)
+    p = (rng.standard_normal(n) * 0.3).astype(dt)
+    g = (rng.standard_normal(n) * 1e-2).astype(dt)
+    mu = (rng.standard_normal(n) * 1e-2).astype(dt)
+    nu = (rng.random(n) * 1e-4).astype(dt)
+    dp = rng.standard_normal(n).astype(dt)
+    dus = rng.standard_normal(n).astype(dt)
+    dme = (rng.standard_normal(n) * 1e-3).astype(dt)
+    dne = (rng.standard_normal(n) * 1e-3).astype(dt)
+    g[::13] = 0
+    mu[::13] = 0
+    return p, g, mu, nu, dp, dus, dme, dne
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_step_kernels_vs_oracle_composition(c_oracle, tag):
+    from oracle import adam_oracle as ao
+    from torchopt_b200 import abi
+    dt = abi.F32 if tag == "f32" else abi.F64
+    s = torch.cuda.current_stream().cuda_stream
+    lr = 3e-3
+    for n in (1, 7, 8, 9, 1023, 4096, 4097, 8193, 70_001):
+        p, g, mu, nu, dp, dus, dme, dne = inputs(n, NP[tag], n)
+        for er, cnt in ((0.0, 1), (1e-8, 4)):
+            P, G, MU, NU, DP, DUS, DME, DNE = map(dev, (p, g, mu, nu, dp, dus, dme, dne))
+            o = [torch.empty_like(P) for _ in range(4)]
+            w_p, w_mu, w_nu, w_us = ao.fused_step_forward(c_oracle, p, g, mu, nu, B1, B2, EPS, er, cnt, -lr)
+            for with_us in (True, False):
+                for t in o:
+                    t.fill_(7.0)
+                abi.step_forward(dt, [P.data_ptr()], [G.data_ptr()], [MU.data_ptr()], [NU.data_ptr()],
+                                 [o[0].data_ptr()], [o[1].data_ptr()], [o[2].data_ptr()],
+                                 [o[3].data_ptr()] if with_us else None, [n], [cnt], B1, B2, EPS, er, -lr, s)
+                assert_bits_equal(host(o[0]), w_p, f"step p' n={n}")
+                assert_bits_equal(host(o[1]), w_mu, f"step mu' n={n}")
+                assert_bits_equal(host(o[2]), w_nu, f"step nu' n={n}")
+                if with_us:
+                    assert_bits_equal(host(o[3]), w_us, f"step us n={n}")
+                else:
+                    assert (host(o[3]) == 7.0).all()
+            # in place
+            a, b, c, d = P.clone(), G.clone(), MU.clone(), NU.clone()
+            abi.step_inplace(dt, [a.data_ptr()], [b.data_ptr()], [c.data_ptr()], [d.data_ptr()], [n], [cnt], B1, B2, EPS,
+                             er, -lr, s)
+            for got, want, name in ((a, w_p, "p"), (b, w_us, "g<-us"), (c, w_mu, "mu"), (d, w_nu, "nu")):
+                assert_bits_equal(host(got), want, f"step_inplace {name} n={n}")
+            # backward: FULL, LAST and GENERIC presence patterns (incl. a gradient on the scaled update)
+            M2, V2 = dev(w_mu), dev(w_nu)
+            for hdp, hdus, hme, hne in ((1, 0, 1, 1), (1, 0, 0, 0), (1, 1, 1, 0), (0, 1, 0, 1), (0, 0, 1, 1), (1, 0, 0, 1)):
+                want = ao.fused_step_backward(c_oracle, dp if hdp else None, w_mu, w_nu, g, dme if hme else None,
+                                              dne if hne else None, B1, B2, EPS, er, cnt, -lr, dus=dus if hdus else None)
+                outs = [torch.full_like(P, 7.0) for _ in range(3)]
+                abi.step_backward(dt, [DP.data_ptr() if hdp else None], [DUS.data_ptr() if hdus else None],
+                                  [M2.data_ptr()], [V2.data_ptr()], [G.data_ptr()], [DME.data_ptr() if hme else None],
+                                  [DNE.data_ptr() if hne else None], [outs[0].data_ptr()], [outs[1].data_ptr()],
+                                  [outs[2].data_ptr()], [n], [cnt], B1, B2, EPS, er, -lr, s)
+                for k in range(3):
+                    got = host(outs[k])
+                    if want[k] is None:
+                        assert (got == 0).all()
+                    else:
+                        assert_bits_equal(got, want[k], f"step bwd out{k} n={n} pattern={(hdp, hdus, hme, hne)}")
+
+
+def _mlp(dtype=torch.float32):
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(20, 33), torch.nn.Tanh(), torch.nn.Linear(33, 7)).to(dtype).cuda()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("mrg", [True, False])
+def test_meta_adam_whole_step_equals_chained_path(dtype, mrg):
+    """MetaAdam with the single whole-step launch vs the chained transformations + torch mul/add: parameters and
+    meta-gradients bit-identical; Adam-kernel launches per inner step stay 1, torch's 2 kernels per leaf disappear."""
+    import torchopt_b200 as tb
+    from torchopt_b200 import optim
+    x = torch.randn(16, 20, device="cuda", dtype=dtype, generator=torch.Generator("cuda").manual_seed(1))
+    y = torch.randn(16, 7, device="cuda", dtype=dtype, generator=torch.Generator("cuda").manual_seed(2))
+    out = {}
+    for fuse in (True, False):
+        optim.FUSE_STEP = fuse
+        try:
+            net = _mlp(dtype)
+            init = list(net.parameters())
+            opt = tb.MetaAdam(net, lr=1e-2, moment_requires_grad=mrg, eps_root=1e-8)
+            before = tb.abi.kernel_launches()
+            for _ in range(4):
+                opt.step(((net(x) - y) ** 2).mean())
+            launches = tb.abi.kernel_launches() - before
+            outer = ((net(x) - y) ** 2).mean()
+            meta = torch.autograd.grad(outer, init)
+            torch.cuda.synchronize()
+            out[fuse] = ([p.detach().cpu().numpy() for p in opt.params()], [m.cpu().numpy() for m in meta], launches,
+                         [m.detach().cpu().numpy() for m in opt.state[0].mu], [int(c) for c in opt.state[0].count])
+        finally:
+            optim.FUSE_STEP = True
+    assert out[True][2] == 4 and out[False][2] == 4
+    assert out[True][4] == out[False][4] == [4, 4, 4, 4]
+    for a, b in zip(out[True][0], out[False][0]):
+        assert_bits_equal(a, b, "unrolled parameters")
+    for a, b in zip(out[True][3], out[False][3]):
+        assert_bits_equal(a, b, "first moments")
+    for a, b in zip(out[True][1], out[False][1]):
+        assert_bits_equal(a, b, "meta-gradients")
+
+
+def test_inplace_adam_whole_step_equals_chained_path():
+    import torchopt_b200 as tb
+    from torchopt_b200 import optim
+    res = {}
+    for fuse in (True, False):
+        optim.FUSE_STEP = fuse
+        try:
+            net = _mlp()
+            opt = tb.Adam(net.parameters(), lr=1e-3, eps_root=1e-8)
+            gen = torch.Generator("cuda").manual_seed(5)
+            for _ in range(3):
+                x = torch.randn(8, 20, device="cuda", generator=gen)
+                opt.zero_grad()
+                net(x).pow(2).mean().backward()
+                opt.step()
+            torch.cuda.synchronize()
+            res[fuse] = ([p.detach().cpu().numpy() for p in net.parameters()],
+                         [p.grad.cpu().numpy() for p in net.parameters()])
+        finally:
+            optim.FUSE_STEP = True
+    for a, b in zip(res[True][0], res[False][0]):
+        assert_bits_equal(a, b, "parameters after in-place steps")
+    for a, b in zip(res[True][1], res[False][1]):
+        assert_bits_equal(a, b, "p.grad holds the scaled update after step, as in the reference's in-place chain")
+
+
+def test_adam_step_none_grads_and_multi_dtype():
+    """Leaves without gradients pass through; fp32 and fp64 leaves in one call are grouped into two launches."""
+    import torchopt_b200 as tb
+    step = tb.AdamStep(step_size=-1e-2, eps_root=1e-8)
+    p = [torch.randn(100, device="cuda"), torch.randn(50, device="cuda", dtype=torch.float64), torch.randn(3, device="cuda")]
+    g = [torch.randn(100, device="cuda"), torch.randn(50, device="cuda", dtype=torch.float64), None]
+    mu = [torch.zeros_like(t) for t in p]
+    nu = [torch.zeros_like(t) for t in p]
+    before = tb.abi.kernel_launches()
+    new_p, new_mu, new_nu = step(p, g, mu, nu, [1, 1, 1])
+    assert tb.abi.kernel_launches() - before == 2
+    assert new_p[2] is p[2] and new_mu[2] is mu[2]
+    for i in (0, 1):
+        m, v, u = tb.AdamOp(eps_root=1e-8, inplace=False)(mu[i], nu[i], g[i], 1)
+        assert torch.equal(new_p[i], p[i] + u * (-1e-2)) and torch.equal(new_mu[i], m) and torch.equal(new_nu[i], v)

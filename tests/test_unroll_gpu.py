@@ -70,12 +70,13 @@ def test_meta_adam_fused_equals_three_node_graph(mrg):
     per-leaf three-node path give bit-identical parameters and meta-gradients; launches drop from 3 per leaf per
     step to 1 per step."""
     import torchopt_b200 as tb
-    from torchopt_b200 import transform
+    from torchopt_b200 import optim, transform
     x = torch.randn(16, 20, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
     y = torch.randn(16, 7, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
     out = {}
     for fused in (True, False):
         transform.FUSED_GRAPH = fused
+        optim.FUSE_STEP = False   # this test is about the chained path (Adam op + torch mul/add)
         try:
             net = _mlp()
             init = [p for p in net.parameters()]
@@ -91,6 +92,7 @@ def test_meta_adam_fused_equals_three_node_graph(mrg):
                           fwd_launches)
         finally:
             transform.FUSED_GRAPH = True
+            optim.FUSE_STEP = True
     assert out[True][2] == 4 and out[False][2] == 4 * 4 * 3
     for a, b in zip(out[True][0], out[False][0]):
         assert_bits_equal(a, b, "unrolled parameters")

@@ -6,10 +6,11 @@ from typing import Iterable, Union
 import torch
 
 from torchopt_b200.accelerated_op.adam_op import AdamOp
+from torchopt_b200.accelerated_op.adam_step import AdamStep
 
 Device = Union[torch.device, str, int]
 
-__all__ = ["AdamOp", "is_available"]
+__all__ = ["AdamOp", "AdamStep", "is_available"]
 
 
 def is_available(devices: Device | Iterable[Device] | None = None) -> bool:

@@ -398,6 +398,186 @@ struct FusedBwd {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// "whole optimizer step" kernels: Adam update + scale(step_size) + apply_updates in one pass
+// ------------------------------------------------------------------------------------------------
+// forward:  mu', nu', u as FusedFwd ; us = u * S (transform/scale.py:86-105: g.mul(step_size)) ;
+//           p' = p + us (update.py:78-79: p.add(u)).  Reads p, g, mu, nu (16 B/elem fp32), writes p', mu', nu'
+//           (12 B) and, only if the caller wants the update tensor, us (4 B).  u itself is never stored: the
+//           backward recomputes it from mu', nu' with the identical instruction sequence (same bits).
+// INPLACE:  p, g, mu, nu updated in place (g <- us), for the non-differentiable Optimizer.step path.
+template <typename T, bool INPLACE>
+struct StepFwd {
+  using CT = T;
+  static constexpr int NPTR = 8, NGS = 7, NLS = 2;
+  struct Leaf {
+    const T *p, *g, *mu, *nu;
+    T *p_o, *mu_o, *nu_o, *us_o;
+    CT B1, OMB1, B2, OMB2, ER, EPS, S, C1, C2;
+  };
+  template <class Tab>
+  static __device__ __forceinline__ Leaf leaf(const Tab &t, int l) {
+    Leaf L;
+    L.p = (const T *)t.ptr[0][l], L.g = (const T *)t.ptr[1][l], L.mu = (const T *)t.ptr[2][l];
+    L.nu = (const T *)t.ptr[3][l];
+    L.p_o = (T *)t.ptr[4][l], L.mu_o = (T *)t.ptr[5][l], L.nu_o = (T *)t.ptr[6][l], L.us_o = (T *)t.ptr[7][l];
+    L.B1 = t.gs[0], L.OMB1 = t.gs[1], L.B2 = t.gs[2], L.OMB2 = t.gs[3], L.ER = t.gs[4], L.EPS = t.gs[5];
+    L.S = t.gs[6];
+    L.C1 = t.ls[0][l], L.C2 = t.ls[1][l];
+    return L;
+  }
+  template <int P>
+  static __device__ __forceinline__ bool aligned(const Leaf &L) {
+    return is_aligned<T, P>(L.p) && is_aligned<T, P>(L.g) && is_aligned<T, P>(L.mu) && is_aligned<T, P>(L.nu) &&
+           is_aligned<T, P>(L.p_o) && is_aligned<T, P>(L.mu_o) && is_aligned<T, P>(L.nu_o) &&
+           is_aligned<T, P>(L.us_o);
+  }
+  template <int P>
+  struct Regs {
+    Pack<T, P> p, g, mu, nu;  // become p', us, mu', nu'
+  };
+  template <int P>
+  static __device__ __forceinline__ void load(Regs<P> &r, const Leaf &L, long long i) {
+    load_pack<!INPLACE>(r.p, L.p + i);
+    load_pack<!INPLACE>(r.g, L.g + i);
+    load_pack<!INPLACE>(r.mu, L.mu + i);
+    load_pack<!INPLACE>(r.nu, L.nu + i);
+  }
+  template <int P>
+  static __device__ __forceinline__ void compute(Regs<P> &r, const Leaf &L) {
+    using M = Math<CT>;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const CT g = r.g.v[k], m = r.mu.v[k], v = r.nu.v[k];
+      const CT m_out = M::add(M::mul(L.B1, m), M::mul(L.OMB1, g));
+      const CT v_out = M::add(M::mul(L.B2, v), M::mul(M::mul(L.OMB2, g), g));
+      const CT u = M::div(M::mul(m_out, L.C1), M::add(M::sqrt(M::add(M::mul(v_out, L.C2), L.ER)), L.EPS));
+      const CT us = M::mul(u, L.S);
+      r.mu.v[k] = m_out;
+      r.nu.v[k] = v_out;
+      r.g.v[k] = us;
+      r.p.v[k] = M::add(r.p.v[k], us);
+    }
+  }
+  template <int P>
+  static __device__ __forceinline__ void store(const Regs<P> &r, const Leaf &L, long long i) {
+    store_pack(L.mu_o + i, r.mu);
+    store_pack(L.nu_o + i, r.nu);
+    if (L.us_o != nullptr) store_pack(L.us_o + i, r.g);
+    store_pack(L.p_o + i, r.p);
+  }
+};
+
+// backward of the whole step.  Incoming: dp' (gradient of the new parameters), dmu_ext, dnu_ext (gradients of the new
+// moments from later steps) and optionally dus (gradient of the returned scaled update, normally absent).
+//   du_s  = dp' (+ dus)            AddBackward of p' = p + us: both inputs receive dp'      (dp = dp' is returned by
+//                                  the binding as the same tensor -- no bytes move)
+//   du    = du_s * S               MulBackward of us = u * S
+//   u     = recomputed from mu', nu' (bit-identical to the forward's u)
+//   then exactly FusedBwd: backward_updates, two-addend accumulations, backward_mu, backward_nu, dg = dg_mu + dg_nu
+// Reads dp', mu', nu', g, dmu_ext, dnu_ext (24 B/elem fp32) and writes dg, dmu, dnu (12 B).
+// MODE as for FusedBwd: BWD_FULL (all three incoming present), BWD_LAST (dp' only), BWD_GENERIC (run-time NULLs).
+template <typename T, int MODE>
+struct StepBwd {
+  using CT = T;
+  static constexpr int NPTR = 10, NGS = 7, NLS = 4;
+  struct Leaf {
+    const T *dp, *dus, *m, *v, *g, *dmu_ext, *dnu_ext;
+    T *dg, *dmu, *dnu;
+    CT B1, OMB1, B2, TWO_OMB2, ER, EPS, S, O1, C2E, C1, C2;
+  };
+  template <class Tab>
+  static __device__ __forceinline__ Leaf leaf(const Tab &t, int l) {
+    Leaf L;
+    L.dp = (const T *)t.ptr[0][l], L.dus = (const T *)t.ptr[1][l], L.m = (const T *)t.ptr[2][l];
+    L.v = (const T *)t.ptr[3][l], L.g = (const T *)t.ptr[4][l];
+    L.dmu_ext = (const T *)t.ptr[5][l], L.dnu_ext = (const T *)t.ptr[6][l];
+    L.dg = (T *)t.ptr[7][l], L.dmu = (T *)t.ptr[8][l], L.dnu = (T *)t.ptr[9][l];
+    L.B1 = t.gs[0], L.OMB1 = t.gs[1], L.B2 = t.gs[2], L.TWO_OMB2 = t.gs[3], L.ER = t.gs[4], L.EPS = t.gs[5];
+    L.S = t.gs[6];
+    L.O1 = t.ls[0][l], L.C2E = t.ls[1][l], L.C1 = t.ls[2][l], L.C2 = t.ls[3][l];
+    return L;
+  }
+  static __device__ __forceinline__ bool has_dp(const Leaf &L) { return MODE != BWD_GENERIC || L.dp != nullptr; }
+  static __device__ __forceinline__ bool has_dus(const Leaf &L) { return MODE == BWD_GENERIC && L.dus != nullptr; }
+  static __device__ __forceinline__ bool has_du(const Leaf &L) { return has_dp(L) || has_dus(L); }
+  static __device__ __forceinline__ bool has_dmu_ext(const Leaf &L) {
+    return MODE == BWD_FULL || (MODE == BWD_GENERIC && L.dmu_ext != nullptr);
+  }
+  static __device__ __forceinline__ bool has_dnu_ext(const Leaf &L) {
+    return MODE == BWD_FULL || (MODE == BWD_GENERIC && L.dnu_ext != nullptr);
+  }
+  static __device__ __forceinline__ bool want_dg(const Leaf &L) { return MODE != BWD_GENERIC || L.dg != nullptr; }
+  static __device__ __forceinline__ bool want_dmu(const Leaf &L) { return MODE != BWD_GENERIC || L.dmu != nullptr; }
+  static __device__ __forceinline__ bool want_dnu(const Leaf &L) { return MODE != BWD_GENERIC || L.dnu != nullptr; }
+  static __device__ __forceinline__ bool need_g(const Leaf &L) {
+    return want_dg(L) && (has_du(L) || has_dnu_ext(L));
+  }
+  template <int P>
+  static __device__ __forceinline__ bool aligned(const Leaf &L) {
+    return is_aligned<T, P>(L.dp) && is_aligned<T, P>(L.dus) && is_aligned<T, P>(L.m) && is_aligned<T, P>(L.v) &&
+           is_aligned<T, P>(L.g) && is_aligned<T, P>(L.dmu_ext) && is_aligned<T, P>(L.dnu_ext) &&
+           is_aligned<T, P>(L.dg) && is_aligned<T, P>(L.dmu) && is_aligned<T, P>(L.dnu);
+  }
+  template <int P>
+  struct Regs {
+    Pack<T, P> dp, dus, m, v, g, dme, dne;  // g -> dg, dme -> dmu, dne -> dnu
+  };
+  template <int P>
+  static __device__ __forceinline__ void load(Regs<P> &r, const Leaf &L, long long i) {
+    if (has_dp(L)) load_pack<true>(r.dp, L.dp + i);
+    if (has_dus(L)) load_pack<true>(r.dus, L.dus + i);
+    if (has_du(L)) {
+      load_pack<true>(r.m, L.m + i);
+      load_pack<true>(r.v, L.v + i);
+    }
+    if (need_g(L)) load_pack<true>(r.g, L.g + i);
+    if (has_dmu_ext(L)) load_pack<true>(r.dme, L.dmu_ext + i);
+    if (has_dnu_ext(L)) load_pack<true>(r.dne, L.dnu_ext + i);
+  }
+  template <int P>
+  static __device__ __forceinline__ void compute(Regs<P> &r, const Leaf &L) {
+    using M = Math<CT>;
+    const bool hdp = has_dp(L), hdus = has_dus(L), hdu = has_du(L), hme = has_dmu_ext(L), hne = has_dnu_ext(L);
+    const bool ng = need_g(L);
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      CT dmu_tot = CT(0), dnu_tot = CT(0);
+      if (hdu) {
+        const CT dus = (hdp && hdus) ? M::add(r.dp.v[k], r.dus.v[k]) : (hdp ? r.dp.v[k] : r.dus.v[k]);
+        const CT du = M::mul(dus, L.S);
+        const CT m = r.m.v[k];
+        const CT u = M::div(M::mul(m, L.C1), M::add(M::sqrt(M::add(M::mul(r.v.v[k], L.C2), L.ER)), L.EPS));
+        CT dm_new = CT(0), dn_new = CT(0);
+        if (m != CT(0)) {
+          const CT q = M::div(u, m);
+          const CT den = M::mul(q, L.O1);
+          dm_new = M::mul(du, q);
+          const CT t = M::mul(M::mul(-du, u), den);
+          dn_new = M::dnu_tail(t, L.C2E, den);
+        }
+        dmu_tot = hme ? M::add(r.dme.v[k], dm_new) : dm_new;
+        dnu_tot = hne ? M::add(r.dne.v[k], dn_new) : dn_new;
+      } else {
+        if (hme) dmu_tot = r.dme.v[k];
+        if (hne) dnu_tot = r.dne.v[k];
+      }
+      const bool have_m = hdu || hme, have_n = hdu || hne;
+      const CT dg_mu = M::mul(L.OMB1, dmu_tot);
+      const CT dg_nu = ng ? M::mul(M::mul(L.TWO_OMB2, r.g.v[k]), dnu_tot) : CT(0);
+      r.g.v[k] = (have_m && have_n) ? M::add(dg_mu, dg_nu) : (have_m ? dg_mu : dg_nu);
+      r.dme.v[k] = have_m ? M::mul(L.B1, dmu_tot) : CT(0);
+      r.dne.v[k] = have_n ? M::mul(L.B2, dnu_tot) : CT(0);
+    }
+  }
+  template <int P>
+  static __device__ __forceinline__ void store(const Regs<P> &r, const Leaf &L, long long i) {
+    if (want_dg(L)) store_pack(L.dg + i, r.g);
+    if (want_dmu(L)) store_pack(L.dmu + i, r.dme);
+    if (want_dnu(L)) store_pack(L.dnu + i, r.dne);
+  }
+};
+
 // ---- the six out-of-place operators of the reference surface (single dtype T for every array) ----
 // Generic 2-in / 2-out shape; unused slots are compiled away through the NIN/NOUT constants.
 enum { OP_FWD_MU = 0, OP_FWD_NU, OP_FWD_UPD, OP_BWD_MU, OP_BWD_NU, OP_BWD_UPD };

@@ -43,7 +43,7 @@ struct Cfg<float, float> {
 };
 template <>
 struct Cfg<double, double> {
-  static constexpr int P_FWD = 4, U_FWD = 2, P_BWD = 4, U_BWD = 1, P_UNF = 4, U_UNF = 2;
+  static constexpr int P_FWD = 4, U_FWD = 1, P_BWD = 4, U_BWD = 1, P_UNF = 4, U_UNF = 2;
 };
 template <>
 struct Cfg<bf16_t, float> {
@@ -167,10 +167,9 @@ static int run_batches(long long num_leaves, long long total_elems, int flags, c
   return launch_table<Op, P, U, BLOCK, MAXL>(tab, di, stream);
 }
 
-template <class Op, int P, int U, class NextFn>
+template <class Op, int P, int U, int BLOCK = B200_ADAM_BLOCK, class NextFn>
 static int run_op(long long num_leaves, long long total_elems, int flags, const typename Op::CT *gs, NextFn &&next,
                   cudaStream_t stream) {
-  constexpr int BLOCK = B200_ADAM_BLOCK;
   if (num_leaves <= 1) return run_batches<Op, P, U, BLOCK, 1>(num_leaves, total_elems, flags, gs, next, stream);
   if (num_leaves <= 64) return run_batches<Op, P, U, BLOCK, 64>(num_leaves, total_elems, flags, gs, next, stream);
   return run_batches<Op, P, U, BLOCK, 256>(num_leaves, total_elems, flags, gs, next, stream);
@@ -297,8 +296,8 @@ static int fused_backward_mode(int64_t L, const void *const *du, const void *con
   };
   using C = Cfg<TG, TS>;
   if constexpr (MODE == BWD_GENERIC) {
-    // run-time presence flags cost registers: use half-width vectors, no unroll (stays spill-free at 512 threads)
-    return run_op<Op, C::P_BWD / 2, 1>(L, total, 0, gs, next, stream);
+    // run-time presence flags cost registers: half-width vectors, no unroll, 256-thread CTAs (spill-free)
+    return run_op<Op, C::P_BWD / 2, 1, 256>(L, total, 0, gs, next, stream);
   } else {
     return run_op<Op, C::P_BWD, C::U_BWD>(L, total, 0, gs, next, stream);
   }
@@ -331,6 +330,123 @@ static int fused_backward_impl(int64_t L, const void *const *du, const void *con
                                                      b1, b2, eps_root, total, stream);
   return fused_backward_mode<TG, TS, CT, BWD_GENERIC>(L, du, u, new_mu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n, count,
                                                       b1, b2, eps_root, total, stream);
+}
+
+// ---- whole-step kernels (Adam + scale(step_size) + apply_updates) ----------------------------------
+template <typename T, bool INPLACE>
+struct StepFwdH : StepFwd<T, INPLACE> {
+  static void advance(void **p, long long k) {
+    for (int a = 0; a < 8; ++a)
+      if (p[a]) p[a] = (char *)p[a] + (size_t)k * sizeof(T);
+  }
+};
+template <typename T, int MODE>
+struct StepBwdH : StepBwd<T, MODE> {
+  static void advance(void **p, long long k) {
+    for (int a = 0; a < 10; ++a)
+      if (p[a]) p[a] = (char *)p[a] + (size_t)k * sizeof(T);
+  }
+};
+
+template <typename T, bool INPLACE>
+static int step_forward_impl(int64_t L, const void *const *p, const void *const *g, const void *const *mu,
+                             const void *const *nu, void *const *p_out, void *const *mu_out, void *const *nu_out,
+                             void *const *us_out, const int64_t *n, const uint64_t *count, double b1, double b2,
+                             double eps, double eps_root, double step_size, cudaStream_t stream) {
+  using Op = StepFwdH<T, INPLACE>;
+  const T B1 = (T)b1, B2 = (T)b2;
+  const T gs[7] = {B1, T(1) - B1, B2, T(1) - B2, (T)eps_root, (T)eps, (T)step_size};
+  long long total = 0;
+  for (int64_t i = 0; i < L; ++i) {
+    if (n[i] < 0) return B200_ADAM_E_ARG;
+    if (n[i] > 0 && (!p[i] || !g[i] || !mu[i] || !nu[i] || !p_out[i] || !mu_out[i] || !nu_out[i]))
+      return B200_ADAM_E_ARG;
+    total += n[i];
+  }
+  uint64_t last_count = ~0ull;
+  T c1 = 0, c2 = 0;
+  auto next = [&](long long i, HostLeaf<Op> &hl) {
+    if (n[i] == 0) return false;
+    if (count[i] != last_count) {
+      last_count = count[i];
+      c1 = (T)inv_one_minus_pow(b1, last_count);
+      c2 = (T)inv_one_minus_pow(b2, last_count);
+    }
+    const void *in[4] = {p[i], g[i], mu[i], nu[i]};
+    for (int a = 0; a < 4; ++a) hl.ptr[a] = const_cast<void *>(in[a]);
+    hl.ptr[4] = p_out[i], hl.ptr[5] = mu_out[i], hl.ptr[6] = nu_out[i], hl.ptr[7] = us_out ? us_out[i] : nullptr;
+    hl.n = n[i];
+    hl.ls[0] = c1, hl.ls[1] = c2;
+    return true;
+  };
+  using C = Cfg<T, T>;
+  return run_op<Op, C::P_FWD, C::U_FWD>(L, total, 0, gs, next, stream);
+}
+
+template <typename T, int MODE>
+static int step_backward_mode(int64_t L, const void *const *dp, const void *const *dus, const void *const *new_mu,
+                              const void *const *new_nu, const void *const *g, const void *const *dmu_ext,
+                              const void *const *dnu_ext, void *const *dg, void *const *dmu, void *const *dnu,
+                              const int64_t *n, const uint64_t *count, double b1, double b2, double eps,
+                              double eps_root, double step_size, long long total, cudaStream_t stream) {
+  using Op = StepBwdH<T, MODE>;
+  const T B1 = (T)b1, B2 = (T)b2;
+  const T gs[7] = {B1, T(1) - B1, B2, T(2) * (T(1) - B2), (T)eps_root, (T)eps, (T)step_size};
+  uint64_t last_count = ~0ull;
+  T o1 = 0, c2e = 0, c1 = 0, c2 = 0;
+  auto next = [&](long long i, HostLeaf<Op> &hl) {
+    if (n[i] == 0) return false;
+    if (!dg[i] && !dmu[i] && !dnu[i]) return false;
+    if (count[i] != last_count) {
+      last_count = count[i];
+      o1 = (T)one_minus_pow(b1, last_count);
+      c2e = (T)inv_one_minus_pow_eps(b2, eps_root, last_count);
+      c1 = (T)inv_one_minus_pow(b1, last_count);
+      c2 = (T)inv_one_minus_pow(b2, last_count);
+    }
+    const void *q[10] = {dp[i], dus ? dus[i] : nullptr, new_mu[i], new_nu[i], g[i], dmu_ext[i], dnu_ext[i],
+                         dg[i], dmu[i], dnu[i]};
+    for (int a = 0; a < 10; ++a) hl.ptr[a] = const_cast<void *>(q[a]);
+    hl.n = n[i];
+    hl.ls[0] = o1, hl.ls[1] = c2e, hl.ls[2] = c1, hl.ls[3] = c2;
+    return true;
+  };
+  using C = Cfg<T, T>;
+  if constexpr (MODE == BWD_GENERIC) {
+    return run_op<Op, C::P_BWD / 2, 1, 256>(L, total, 0, gs, next, stream);
+  } else {
+    return run_op<Op, C::P_BWD, C::U_BWD>(L, total, 0, gs, next, stream);
+  }
+}
+
+template <typename T>
+static int step_backward_impl(int64_t L, const void *const *dp, const void *const *dus, const void *const *new_mu,
+                              const void *const *new_nu, const void *const *g, const void *const *dmu_ext,
+                              const void *const *dnu_ext, void *const *dg, void *const *dmu, void *const *dnu,
+                              const int64_t *n, const uint64_t *count, double b1, double b2, double eps,
+                              double eps_root, double step_size, cudaStream_t stream) {
+  bool all_full = true, all_last = true;
+  long long total = 0;
+  for (int64_t i = 0; i < L; ++i) {
+    if (n[i] < 0) return B200_ADAM_E_ARG;
+    if (n[i] == 0) continue;
+    total += n[i];
+    const bool hdp = dp[i] != nullptr, hdus = dus && dus[i] != nullptr;
+    const bool hme = dmu_ext[i] != nullptr, hne = dnu_ext[i] != nullptr;
+    if ((hdp || hdus) && (!new_mu[i] || !new_nu[i])) return B200_ADAM_E_ARG;
+    if (dg[i] && (hdp || hdus || hne) && !g[i]) return B200_ADAM_E_ARG;
+    const bool outs = dg[i] && dmu[i] && dnu[i];
+    all_full = all_full && hdp && !hdus && hme && hne && outs;
+    all_last = all_last && hdp && !hdus && !hme && !hne && outs;
+  }
+  if (total == 0) return 0;
+#define B200_STEP_BWD(MODE)                                                                                      \
+  step_backward_mode<T, MODE>(L, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n, count, b1, b2, eps, \
+                              eps_root, step_size, total, stream)
+  if (all_full) return B200_STEP_BWD(BWD_FULL);
+  if (all_last) return B200_STEP_BWD(BWD_LAST);
+  return B200_STEP_BWD(BWD_GENERIC);
+#undef B200_STEP_BWD
 }
 
 // ---- un-fused single-tensor operators --------------------------------------------------------------
@@ -441,7 +557,7 @@ int b200_adam_query_launch(int dtype, int backward, int64_t n, int32_t out[5]) {
   const long long chunks = (n + chunk - 1) / chunk;
   long long grid = chunks;
   if (per_sm > 0 && (long long)di.sms * per_sm < grid) grid = (long long)di.sms * per_sm;
-  (void)occ;
+  (void)occ;  // occupancy is informational only since the default grid is non-persistent
   out[0] = (int32_t)grid, out[1] = BLOCK, out[2] = chunk, out[3] = P, out[4] = U;
   return 0;
 }
@@ -530,6 +646,67 @@ int b200_adam_backward_updates(int dtype, const void *dupdates, const void *upda
   (void)b2;
   const double o1 = one_minus_pow(b1, count), c2e = inv_one_minus_pow_eps(b2, eps_root, count);
   B200_UNFUSED_DISPATCH(OP_BWD_UPD, dupdates, updates, new_mu, dnew_mu_out, dnew_nu_out, o1, c2e, 0, 0)
+}
+
+
+static int step_forward_dispatch(bool inplace, int dtype, int64_t L, const void *const *p, const void *const *g,
+                                 const void *const *mu, const void *const *nu, void *const *p_out,
+                                 void *const *mu_out, void *const *nu_out, void *const *us_out, const int64_t *n,
+                                 const uint64_t *count, double b1, double b2, double eps, double eps_root,
+                                 double step_size, void *stream) {
+  if (L < 0) return B200_ADAM_E_ARG;
+  if (L == 0) return 0;
+  if (!p || !g || !mu || !nu || !p_out || !mu_out || !nu_out || !n || !count) return B200_ADAM_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+#ifndef B200_ADAM_TUNE_F32_ONLY
+  if (dtype == B200_ADAM_F64)
+    return inplace ? step_forward_impl<double, true>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
+                                                     eps, eps_root, step_size, s)
+                   : step_forward_impl<double, false>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
+                                                      eps, eps_root, step_size, s);
+#endif
+  if (dtype == B200_ADAM_F32)
+    return inplace ? step_forward_impl<float, true>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
+                                                    eps, eps_root, step_size, s)
+                   : step_forward_impl<float, false>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
+                                                     eps, eps_root, step_size, s);
+  return B200_ADAM_E_DTYPE;
+}
+
+int b200_adam_step_forward(int dtype, int64_t num_leaves, const void *const *p, const void *const *g,
+                           const void *const *mu, const void *const *nu, void *const *p_out, void *const *mu_out,
+                           void *const *nu_out, void *const *us_out, const int64_t *n, const uint64_t *count,
+                           double b1, double b2, double eps, double eps_root, double step_size, void *stream) {
+  return step_forward_dispatch(false, dtype, num_leaves, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
+                               eps, eps_root, step_size, stream);
+}
+
+int b200_adam_step_inplace(int dtype, int64_t num_leaves, void *const *p, void *const *g, void *const *mu,
+                           void *const *nu, const int64_t *n, const uint64_t *count, double b1, double b2, double eps,
+                           double eps_root, double step_size, void *stream) {
+  return step_forward_dispatch(true, dtype, num_leaves, p, g, mu, nu, p, mu, nu, g, n, count, b1, b2, eps, eps_root,
+                               step_size, stream);
+}
+
+int b200_adam_step_backward(int dtype, int64_t num_leaves, const void *const *dp, const void *const *dus,
+                            const void *const *new_mu, const void *const *new_nu, const void *const *g,
+                            const void *const *dmu_ext, const void *const *dnu_ext, void *const *dg, void *const *dmu,
+                            void *const *dnu, const int64_t *n, const uint64_t *count, double b1, double b2,
+                            double eps, double eps_root, double step_size, void *stream) {
+  if (num_leaves < 0) return B200_ADAM_E_ARG;
+  if (num_leaves == 0) return 0;
+  if (!dp || !new_mu || !new_nu || !g || !dmu_ext || !dnu_ext || !dg || !dmu || !dnu || !n || !count)
+    return B200_ADAM_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+#ifndef B200_ADAM_TUNE_F32_ONLY
+  if (dtype == B200_ADAM_F64)
+    return step_backward_impl<double>(num_leaves, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n, count,
+                                      b1, b2, eps, eps_root, step_size, s);
+#endif
+  if (dtype == B200_ADAM_F32)
+    return step_backward_impl<float>(num_leaves, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n, count,
+                                     b1, b2, eps, eps_root, step_size, s);
+  return B200_ADAM_E_DTYPE;
 }
 
 }  // extern "C"

@@ -275,6 +275,125 @@ std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor
   return {dg, dmu, dnu};
 }
 
+// ---- whole optimizer step: Adam + scale(step_size) + apply_updates (fp32 / fp64) -------------------------
+// Differentiable form: returns (new_params, new_mu, new_nu, scaled_updates?) for leaves whose gradient is not None;
+// leaves without a gradient pass (param, mu, nu, None) through.  `inplace` mutates params/grads/mu/nu instead.
+std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>, std::vector<OptTensor>> fused_step(
+    const std::vector<Tensor> &params, const std::vector<OptTensor> &grads, const std::vector<Tensor> &mu,
+    const std::vector<Tensor> &nu, double b1, double b2, double eps, double eps_root, double step_size,
+    const std::vector<size_t> &count, bool inplace, bool want_updates) {
+  const size_t L = params.size();
+  if (grads.size() != L || mu.size() != L || nu.size() != L || count.size() != L)
+    throw std::runtime_error("fused_step: params, grads, mu, nu and count must have the same number of leaves");
+  std::vector<Tensor> new_p(L), new_mu(L), new_nu(L);
+  std::vector<OptTensor> new_us(L);
+  std::map<GroupKey, std::vector<size_t>> groups;
+  for (size_t i = 0; i < L; ++i) {
+    if (!grads[i].has_value()) {
+      new_p[i] = params[i], new_mu[i] = mu[i], new_nu[i] = nu[i];
+      continue;
+    }
+    require_cuda(params[i]);
+    const int dt = family(*grads[i], mu[i], "adamStepCUDA", false);
+    same_type(mu[i], nu[i]), same_type(mu[i], params[i]);
+    groups[GroupKey{(int)params[i].device().index(), dt}].push_back(i);
+  }
+  for (auto &kv : groups) {
+    const auto &idx = kv.second;
+    const size_t G = idx.size();
+    std::vector<const void *> pp(G), pg(G), pmu(G), pnu(G);
+    std::vector<void *> op(G), omu(G), onu(G), ous(G);
+    std::vector<int64_t> n(G);
+    std::vector<uint64_t> cnt(G);
+    Ctx c(params[idx[0]]);
+    for (size_t k = 0; k < G; ++k) {
+      const size_t i = idx[k];
+      const Tensor &g = *grads[i];
+      if (inplace) {
+        new_p[i] = params[i], new_mu[i] = mu[i], new_nu[i] = nu[i], new_us[i] = g;
+      } else {
+        new_p[i] = at::empty_like(params[i]), new_mu[i] = at::empty_like(mu[i]), new_nu[i] = at::empty_like(nu[i]);
+        if (want_updates) new_us[i] = at::empty_like(g);
+      }
+      pp[k] = params[i].data_ptr(), pg[k] = g.data_ptr(), pmu[k] = mu[i].data_ptr(), pnu[k] = nu[i].data_ptr();
+      op[k] = new_p[i].data_ptr(), omu[k] = new_mu[i].data_ptr(), onu[k] = new_nu[i].data_ptr();
+      ous[k] = new_us[i] ? new_us[i]->data_ptr() : nullptr;
+      n[k] = g.numel(), cnt[k] = count[i];
+    }
+    if (inplace) {
+      check(b200_adam_step_inplace(kv.first.dtype, (int64_t)G, op.data(), ous.data(), omu.data(), onu.data(), n.data(),
+                                   cnt.data(), b1, b2, eps, eps_root, step_size, c.stream),
+            "fused_step (inplace)");
+    } else {
+      check(b200_adam_step_forward(kv.first.dtype, (int64_t)G, pp.data(), pg.data(), pmu.data(), pnu.data(), op.data(),
+                                   omu.data(), onu.data(), ous.data(), n.data(), cnt.data(), b1, b2, eps, eps_root,
+                                   step_size, c.stream),
+            "fused_step");
+    }
+  }
+  return {new_p, new_mu, new_nu, new_us};
+}
+
+// Backward of fused_step: incoming gradients of (new_params, scaled_updates, new_mu, new_nu), saved (new_mu, new_nu,
+// grads).  Returns (dgrads, dmu, dnu); the gradient w.r.t. params is dparams itself and is handled by the caller.
+std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor>> fused_step_backward(
+    const std::vector<OptTensor> &dparams, const std::vector<OptTensor> &dus, const std::vector<OptTensor> &dmu_ext,
+    const std::vector<OptTensor> &dnu_ext, const std::vector<Tensor> &new_mu, const std::vector<Tensor> &new_nu,
+    const std::vector<Tensor> &g, const std::vector<bool> &need_dg, const std::vector<bool> &need_dmu,
+    const std::vector<bool> &need_dnu, double b1, double b2, double eps, double eps_root, double step_size,
+    const std::vector<size_t> &count) {
+  const size_t L = g.size();
+  if (dparams.size() != L || dus.size() != L || dmu_ext.size() != L || dnu_ext.size() != L || new_mu.size() != L ||
+      new_nu.size() != L || need_dg.size() != L || need_dmu.size() != L || need_dnu.size() != L || count.size() != L)
+    throw std::runtime_error("fused_step_backward: all per-leaf lists must have the same length");
+  std::vector<OptTensor> dg(L), dmu(L), dnu(L);
+  std::vector<Tensor> cdp(L), cdus(L), cme(L), cne(L);
+  std::map<GroupKey, std::vector<size_t>> groups;
+  for (size_t i = 0; i < L; ++i) {
+    const bool hdu = dparams[i].has_value() || dus[i].has_value();
+    const bool hme = dmu_ext[i].has_value(), hne = dnu_ext[i].has_value();
+    if (!hdu && !hme && !hne) continue;
+    const bool wg = need_dg[i], wm = need_dmu[i] && (hdu || hme), wn = need_dnu[i] && (hdu || hne);
+    if (!wg && !wm && !wn) continue;
+    require_cuda(g[i]);
+    const int dt = family(g[i], new_mu[i], "adamStepBackwardCUDA", false);
+    if (dparams[i]) cdp[i] = dparams[i]->contiguous(), same_type(cdp[i], g[i]);
+    if (dus[i]) cdus[i] = dus[i]->contiguous(), same_type(cdus[i], g[i]);
+    if (hme) cme[i] = dmu_ext[i]->contiguous(), same_type(cme[i], g[i]);
+    if (hne) cne[i] = dnu_ext[i]->contiguous(), same_type(cne[i], g[i]);
+    if (wg) dg[i] = at::empty_like(g[i]);
+    if (wm) dmu[i] = at::empty_like(new_mu[i]);
+    if (wn) dnu[i] = at::empty_like(new_nu[i]);
+    groups[GroupKey{(int)g[i].device().index(), dt}].push_back(i);
+  }
+  for (auto &kv : groups) {
+    const auto &idx = kv.second;
+    const size_t G = idx.size();
+    std::vector<const void *> pdp(G), pdus(G), pm(G), pv(G), pg(G), pme(G), pne(G);
+    std::vector<void *> odg(G), odm(G), odn(G);
+    std::vector<int64_t> n(G);
+    std::vector<uint64_t> cnt(G);
+    Ctx c(g[idx[0]]);
+    for (size_t k = 0; k < G; ++k) {
+      const size_t i = idx[k];
+      pdp[k] = cdp[i].defined() ? cdp[i].data_ptr() : nullptr;
+      pdus[k] = cdus[i].defined() ? cdus[i].data_ptr() : nullptr;
+      pme[k] = cme[i].defined() ? cme[i].data_ptr() : nullptr;
+      pne[k] = cne[i].defined() ? cne[i].data_ptr() : nullptr;
+      pm[k] = new_mu[i].data_ptr(), pv[k] = new_nu[i].data_ptr(), pg[k] = g[i].data_ptr();
+      odg[k] = dg[i] ? dg[i]->data_ptr() : nullptr;
+      odm[k] = dmu[i] ? dmu[i]->data_ptr() : nullptr;
+      odn[k] = dnu[i] ? dnu[i]->data_ptr() : nullptr;
+      n[k] = g[i].numel(), cnt[k] = count[i];
+    }
+    check(b200_adam_step_backward(kv.first.dtype, (int64_t)G, pdp.data(), pdus.data(), pm.data(), pv.data(), pg.data(),
+                                  pme.data(), pne.data(), odg.data(), odm.data(), odn.data(), n.data(), cnt.data(), b1,
+                                  b2, eps, eps_root, step_size, c.stream),
+          "fused_step_backward");
+  }
+  return {dg, dmu, dnu};
+}
+
 // host-buffer step (CPU tensors in, CPU tensors out, work done on the current CUDA device)
 std::array<Tensor, 6> host_step(const Tensor &g, const Tensor &mu, const Tensor &nu, const Tensor &du,
                                 const Tensor &dmu_ext, const Tensor &dnu_ext, std::array<Tensor, 6> out, double b1,
@@ -325,6 +444,14 @@ PYBIND11_MODULE(_C, mod) {
         py::arg("dupdates"), py::arg("dmu_ext"), py::arg("dnu_ext"), py::arg("new_updates"), py::arg("new_mu"),
         py::arg("updates"), py::arg("need_dupdates"), py::arg("need_dmu"), py::arg("need_dnu"), py::arg("b1"),
         py::arg("b2"), py::arg("eps_root"), py::arg("count"));
+  m.def("fused_step", &fused_step, "Adam update + scale(step_size) + apply_updates over all leaves (one launch)",
+        py::arg("params"), py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("b1"), py::arg("b2"),
+        py::arg("eps"), py::arg("eps_root"), py::arg("step_size"), py::arg("count"), py::arg("inplace") = false,
+        py::arg("want_updates") = false);
+  m.def("fused_step_backward", &fused_step_backward, "Backward of fused_step over all leaves (one launch)",
+        py::arg("dparams"), py::arg("dscaled_updates"), py::arg("dmu_ext"), py::arg("dnu_ext"), py::arg("new_mu"),
+        py::arg("new_nu"), py::arg("updates"), py::arg("need_dupdates"), py::arg("need_dmu"), py::arg("need_dnu"),
+        py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("step_size"), py::arg("count"));
   m.def("host_step", &host_step, "Fused forward+backward over pinned HOST tensors (pipelined H2D/compute/D2H)",
         py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("dupdates"), py::arg("dmu_ext"), py::arg("dnu_ext"),
         py::arg("out"), py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("count"),

@@ -14,7 +14,13 @@ from typing import Any, Iterable, Sequence
 import torch
 from torch import nn
 
-from torchopt_b200.transform import GradientTransformation, scale_by_accelerated_adam
+from torchopt_b200.accelerated_op.adam_step import AdamStep
+from torchopt_b200.transform import (GradientTransformation, ScaleByAdamState, inc_count_flat,
+                                     scale_by_accelerated_adam)
+
+# A/B switch for parity tests: False makes MetaAdam / Adam run the chained transformations + apply_updates
+# (one Adam launch + 2 torch kernels per leaf per step) instead of the single whole-step launch.
+FUSE_STEP = True
 
 
 def chain_flat(*transforms: GradientTransformation) -> GradientTransformation:
@@ -104,6 +110,15 @@ def apply_updates(params: Sequence, updates: Sequence, *, inplace: bool = True) 
     return out
 
 
+def _fused_chain_step(step_op: AdamStep, params: list, grads: list, state: tuple) -> tuple[list, tuple]:
+    """One whole-step launch for the chain (scale_by_accelerated_adam, scale(-lr)) + apply_updates.
+    ``state`` is the chain's state tuple ``(ScaleByAdamState, ())``; the same structure is returned."""
+    adam_state = state[0]
+    count_inc = inc_count_flat(grads, adam_state.count)
+    new_params, new_mu, new_nu = step_op(params, grads, adam_state.mu, adam_state.nu, count_inc)
+    return new_params, (ScaleByAdamState(mu=new_mu, nu=new_nu, count=count_inc), *state[1:])
+
+
 class MetaAdam:
     """Differentiable Adam over an ``nn.Module`` (optim/meta/adam.py:33-92 + optim/meta/base.py:35-129).
 
@@ -118,6 +133,9 @@ class MetaAdam:
                  moment_requires_grad: bool = True, maximize: bool = False, use_accelerated_op: bool = True) -> None:
         self.impl = adam(lr, betas, eps, weight_decay, eps_root=eps_root, moment_requires_grad=moment_requires_grad,
                          maximize=maximize, use_accelerated_op=use_accelerated_op)
+        # whole-step fusion applies when the chain is exactly [scale_by_accelerated_adam, scale(-lr)]
+        self.fusable = weight_decay == 0.0 and not maximize and not callable(lr)
+        self.step_op = AdamStep(betas[0], betas[1], eps, eps_root=eps_root, step_size=-lr) if self.fusable else None
         self.module = module
         # (owner module, attribute name) for every parameter slot, in named_parameters order
         self.slots = [(m, name) for m in module.modules() for name, p in m._parameters.items() if p is not None]
@@ -131,9 +149,52 @@ class MetaAdam:
         if self.state is None:
             self.state = self.impl.init(flat)
         grads = torch.autograd.grad(loss, flat, create_graph=True, allow_unused=True)
-        updates, self.state = self.impl.update(list(grads), self.state, params=flat, inplace=False)
-        for (m, name), p in zip(self.slots, apply_updates(flat, updates, inplace=False)):
+        if self.fusable and FUSE_STEP:
+            new_params, self.state = _fused_chain_step(self.step_op, flat, list(grads), self.state)
+        else:
+            updates, self.state = self.impl.update(list(grads), self.state, params=flat, inplace=False)
+            new_params = apply_updates(flat, updates, inplace=False)
+        for (m, name), p in zip(self.slots, new_params):
             m._parameters[name] = p
+
+    def state_dict(self) -> Any:
+        return self.state
+
+    def load_state_dict(self, state: Any) -> None:
+        self.state = state
+
+
+class FuncAdam:
+    """Functional Adam over explicit parameter lists (optim/func/base.py:36-120 + optim/func ``FuncAdam``):
+    ``new_params = opt.step(loss, params)``.  ``apply_gradients`` is the same step for gradients already at hand.
+    Uses the single whole-step launch when the recipe has no weight decay / maximize."""
+
+    # pylint: disable-next=too-many-arguments
+    def __init__(self, lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, *, eps_root: float = 0.0, moment_requires_grad: bool = False,
+                 maximize: bool = False, use_accelerated_op: bool = True) -> None:
+        self.impl = adam(lr, betas, eps, weight_decay, eps_root=eps_root, moment_requires_grad=moment_requires_grad,
+                         maximize=maximize, use_accelerated_op=use_accelerated_op)
+        self.fusable = weight_decay == 0.0 and not maximize and not callable(lr)
+        self.hyper = (betas[0], betas[1], eps, eps_root, -lr)
+        self.state = None
+
+    def apply_gradients(self, grads: Sequence, params: Sequence, inplace: bool = False) -> list:
+        params = list(params)
+        if self.state is None:
+            self.state = self.impl.init(params)
+        if self.fusable and FUSE_STEP:
+            b1, b2, eps, eps_root, step_size = self.hyper
+            op = AdamStep(b1, b2, eps, eps_root=eps_root, step_size=step_size, inplace=inplace)
+            new_params, self.state = _fused_chain_step(op, params, list(grads), self.state)
+            return new_params
+        updates, self.state = self.impl.update(list(grads), self.state, params=params, inplace=inplace)
+        return apply_updates(params, updates, inplace=inplace)
+
+    def step(self, loss: torch.Tensor, params: Sequence, inplace: bool = False) -> list:
+        params = list(params)
+        grads = torch.autograd.grad(loss, params, create_graph=not inplace, allow_unused=True)
+        return self.apply_gradients(grads, params, inplace=inplace)
 
     def state_dict(self) -> Any:
         return self.state
@@ -152,6 +213,9 @@ class Adam:
         self.params = list(params)
         self.impl = adam(lr, betas, eps, weight_decay, eps_root=eps_root, maximize=maximize,
                          use_accelerated_op=use_accelerated_op)
+        self.fusable = weight_decay == 0.0 and not maximize and not callable(lr)
+        self.step_op = (AdamStep(betas[0], betas[1], eps, eps_root=eps_root, step_size=-lr, inplace=True)
+                        if self.fusable else None)
         self.state = self.impl.init(self.params)
 
     def zero_grad(self, set_to_none: bool = False) -> None:
@@ -165,5 +229,8 @@ class Adam:
     @torch.no_grad()
     def step(self) -> None:
         grads = [p.grad for p in self.params]
-        updates, self.state = self.impl.update(grads, self.state, params=self.params, inplace=True)
-        apply_updates(self.params, updates, inplace=True)
+        if self.fusable and FUSE_STEP:
+            _, self.state = _fused_chain_step(self.step_op, self.params, grads, self.state)
+        else:
+            updates, self.state = self.impl.update(grads, self.state, params=self.params, inplace=True)
+            apply_updates(self.params, updates, inplace=True)
