@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--n-total", type=int, default=N_TOTAL, help="elements of the whole flat state (default 2^30)")
     ap.add_argument("--e2e-elems", type=int, default=1 << 27, help="elements per rank of the host-buffer e2e leg")
     ap.add_argument("--cpu-elems", type=int, default=1 << 26, help="elements of the bounded CPU-baseline sample")
+    ap.add_argument("--e2e-slice", type=int, default=0, help="slice elements of the host pipeline (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary (ResNet-18 pytree) measurement")
@@ -362,7 +363,8 @@ def run_b200(args) -> None:
         hout = [torch.empty(m).pin_memory() for _ in range(6)]
 
         def host_step():
-            tb.adam_op.host_step(hin[0], hin[1], hin[2], hin[3], hin[4], hin[5], hout, B1, B2, EPS, EPS_ROOT, COUNT)
+            tb.adam_op.host_step(hin[0], hin[1], hin[2], hin[3], hin[4], hin[5], hout, B1, B2, EPS, EPS_ROOT, COUNT,
+                                 args.e2e_slice)
 
         for _ in range(2):
             host_step()

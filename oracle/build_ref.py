@@ -69,6 +69,55 @@ def build(force: bool = False, verbose: bool = True) -> str | None:
     return OUT
 
 
+CUDA_OUT_DIR = os.path.join(OUT_DIR, "cuda")
+CUDA_OUT = os.path.join(CUDA_OUT_DIR, "_C.so")
+CUDA_SOURCE = "src/adam_op/adam_op_impl_cuda.cu"
+
+
+def build_cuda(force: bool = False, verbose: bool = True) -> str | None:
+    """Optional comparison point "O4": the reference's UNMODIFIED CUDA adam_op (src/adam_op/adam_op_impl_cuda.cu,
+    -D__USE_CUDA__) compiled as is for sm_100 -> oracle/_ref/cuda/_C.so.  Used only by tools/leaf_sweep.py to time
+    "the reference's generic kernels recompiled for B200" beside this repo's kernels.  ~4 minutes of nvcc."""
+    srcs = SOURCES + [CUDA_SOURCE]
+    if not all(os.path.isfile(os.path.join(REF, s)) for s in srcs):
+        return CUDA_OUT if os.path.isfile(CUDA_OUT) else None
+    if not force and os.path.isfile(CUDA_OUT):
+        return CUDA_OUT
+    import pybind11
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    os.makedirs(CUDA_OUT_DIR, exist_ok=True)
+    torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    inc = [REF, pybind11.get_include(), sysconfig.get_paths()["include"], *ce.include_paths(),
+           "/usr/local/cuda/include"]
+    defs = [f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", "-DTORCH_API_INCLUDE_EXTENSION_H",
+            "-DTORCH_EXTENSION_NAME=_C", "-D__USE_CUDA__"]
+    objs = []
+    for src in srcs:
+        obj = os.path.join(CUDA_OUT_DIR, src.replace("/", "_") + ".o")
+        if src.endswith(".cu"):
+            cmd = ["nvcc", "-std=c++17", "-O3", "-gencode", "arch=compute_100,code=sm_100", "-Xcompiler", "-fPIC",
+                   "-Xcompiler", "-fopenmp", "-w", "--expt-relaxed-constexpr", *defs, *[f"-I{p}" for p in inc],
+                   "-c", os.path.join(REF, src), "-o", obj]
+        else:
+            cmd = ["g++", "-std=c++17", "-O3", "-fopenmp", "-fPIC", "-w", *defs, *[f"-I{p}" for p in inc], "-c",
+                   os.path.join(REF, src), "-o", obj]
+        if verbose:
+            print("[oracle/_ref/cuda]", cmd[0], "...", src, flush=True)
+        subprocess.check_call(cmd)
+        objs.append(obj)
+    link = ["g++", "-shared", *objs, "-o", CUDA_OUT, f"-L{torch_lib}", f"-Wl,-rpath,{torch_lib}",
+            "-ltorch_python", "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda",
+            "-L/usr/local/cuda/lib64", "-lcudart", "-L/usr/lib/gcc/x86_64-linux-gnu/13", "-lgomp"]
+    subprocess.check_call(link)
+    for o in objs:
+        os.remove(o)
+    return CUDA_OUT
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv)
     print(path if path else "reference sources not present and no prebuilt oracle/_ref/_C.so")
+    if "--cuda" in sys.argv:
+        print(build_cuda(force="--force" in sys.argv))
