@@ -1,0 +1,173 @@
+"""The reference's own test recipes for this path, re-run on CUDA against the B200 operator.
+
+Mirrors /root/reference/tests/test_alias.py:207-270 (functional adam vs torch.optim.Adam, fp64, the full grid of
+lr x betas x inplace x weight_decay x maximize), tests/test_accelerated_op.py:65-113 (accelerated vs the plain
+torch-op scale_by_adam) and tests/test_meta_optim.py:25-90 / test_accelerated_op.py:116-208 (MAML inner loops -- which
+in the reference end without an assertion; here they assert).  Fixture shape follows tests/helpers.py:146-174: an MLP
+with BatchNorm, one parameter and one sub-module that never receive a gradient, five batches, all-zero inputs (so
+first-layer weight gradients are exactly 0 and the ``mu' == 0`` branch of the backward is exercised) plus random ones.
+Tolerances: parameter deltas from the initial model at 25x torch's defaults (tests/helpers.py:203-229).
+"""
+from __future__ import annotations
+
+import itertools
+
+import pytest
+
+torch = pytest.importorskip("torch")
+from torch import nn  # noqa: E402
+from torch.func import functional_call  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+NUM_UPDATES = 5
+
+
+class Net(nn.Module):
+    def __init__(self, batch_norm=True):
+        super().__init__()
+        # With all-zero inputs BatchNorm sees a zero-variance batch, so the first bias gradient is pure round-off noise
+        # that Adam's normalisation amplifies to O(lr): two evaluations on a GPU (non-deterministic reductions) then
+        # disagree by construction.  The zero-input variant therefore drops BatchNorm; it still has exactly-zero
+        # first-layer weight gradients, which is what the fixture is for.
+        norm = (lambda: nn.BatchNorm1d(64)) if batch_norm else nn.Identity
+        self.body = nn.Sequential(nn.Linear(784, 64), norm(), nn.ReLU(), nn.Linear(64, 64), norm(), nn.ReLU(),
+                                  nn.Linear(64, 10))
+        self.unused_module = nn.Linear(3, 3)          # never called -> grads are None
+        self.unused_param = nn.Parameter(torch.zeros(7))
+
+    def forward(self, x):
+        return self.body(x)
+
+
+def make(dtype, zero_inputs, batch_norm=None):
+    torch.manual_seed(42)
+    batch_norm = (not zero_inputs) if batch_norm is None else batch_norm
+    model = Net(batch_norm=batch_norm).to(dtype).cuda()
+    for m in model.modules():
+        if isinstance(m, nn.Linear):
+            nn.init.orthogonal_(m.weight)
+    ref = Net(batch_norm=batch_norm).to(dtype).cuda()
+    ref.load_state_dict(model.state_dict())
+    gen = torch.Generator("cuda").manual_seed(7)
+    loader = []
+    for _ in range(NUM_UPDATES):
+        x = (torch.zeros(64, 784, device="cuda", dtype=dtype) if zero_inputs
+             else torch.randn(64, 784, device="cuda", dtype=dtype, generator=gen))
+        loader.append((x, torch.randint(0, 10, (64,), device="cuda", generator=gen)))
+    return model, ref, loader
+
+
+def assert_close_deltas(params, ref_params, base_params, dtype):
+    rtol, atol = {torch.float64: (1e-7, 1e-7), torch.float32: (1.3e-6, 1e-5)}[dtype]
+    for p, r, b in zip(params, ref_params, base_params):
+        torch.testing.assert_close(p - b, r - b, rtol=rtol * 5 * NUM_UPDATES, atol=atol * 5 * NUM_UPDATES)
+
+
+GRID = list(itertools.product([1e-2, 1e-3, 1e-4], [(0.9, 0.999), (0.95, 0.9995)], [True, False], [0.0, 1e-2],
+                              [False, True]))
+
+
+@pytest.mark.parametrize("zero_inputs", [True, False])
+def test_functional_adam_vs_torch_optim_fp64_grid(zero_inputs):
+    import torchopt_b200 as tb
+    dtype = torch.float64
+    for lr, betas, inplace, wd, maximize in GRID:
+        model, ref, loader = make(dtype, zero_inputs)
+        names = [n for n, _ in model.named_parameters()]
+        base = [p.detach().clone() for p in model.parameters()]
+        params = [p.detach().clone().requires_grad_(True) for p in model.parameters()]
+        buffers = dict(model.named_buffers())
+        opt = tb.adam(lr, betas=betas, eps=1e-8, eps_root=0.0, weight_decay=wd, maximize=maximize)
+        state = opt.init(params)
+        opt_ref = torch.optim.Adam(ref.parameters(), lr, betas=betas, eps=1e-8, weight_decay=wd, maximize=maximize)
+        for xs, ys in loader:
+            pred = functional_call(model, {**dict(zip(names, params)), **buffers}, (xs,))
+            loss = nn.functional.cross_entropy(pred, ys)
+            grads = torch.autograd.grad(loss, params, allow_unused=True)
+            assert any(g is None for g in grads)
+            updates, state = opt.update(list(grads), state, params=params, inplace=inplace)
+            params = tb.apply_updates(params, updates, inplace=inplace)
+            if not inplace:
+                params = [p.detach().requires_grad_(True) for p in params]
+            opt_ref.zero_grad()
+            nn.functional.cross_entropy(ref(xs), ys).backward()
+            opt_ref.step()
+        assert_close_deltas(params, list(ref.parameters()), base, dtype)
+
+
+def plain_scale_by_adam_step(g, mu, nu, count, b1, b2, eps, eps_root):
+    """The non-accelerated recipe (reference transform/scale_by_adam.py:83-222) in plain torch ops."""
+    mu = mu * b1 + g * (1 - b1)
+    nu = nu * b2 + g * g * (1 - b2)
+    mu_hat = mu / (1 - b1 ** count)
+    nu_hat = nu / (1 - b2 ** count)
+    return mu_hat / (torch.sqrt(nu_hat + eps_root) + eps), mu, nu
+
+
+@pytest.mark.parametrize("dtype,inplace", [(torch.float64, True), (torch.float64, False), (torch.float32, False)])
+@pytest.mark.parametrize("lr", [1e-2, 1e-3, 1e-4])
+def test_accelerated_vs_plain_scale_by_adam(dtype, inplace, lr):
+    import torchopt_b200 as tb
+    # fp32: a bias feeding BatchNorm has a mathematically zero gradient, i.e. fp32 round-off noise of the order of eps,
+    # which Adam turns into O(lr) steps that no two implementations reproduce; keep BatchNorm for fp64 only.
+    model, _, loader = make(dtype, zero_inputs=False, batch_norm=dtype is torch.float64)
+    names = [n for n, _ in model.named_parameters()]
+    buffers = dict(model.named_buffers())
+    base = [p.detach().clone() for p in model.parameters()]
+    params = [p.detach().clone().requires_grad_(True) for p in model.parameters()]
+    params_ref = [p.detach().clone().requires_grad_(True) for p in model.parameters()]
+    opt = tb.adam(lr)
+    state = opt.init(params)
+    mu = [torch.zeros_like(p) for p in params_ref]
+    nu = [torch.zeros_like(p) for p in params_ref]
+    for step, (xs, ys) in enumerate(loader, 1):
+        for ps, accelerated in ((params, True), (params_ref, False)):
+            pred = functional_call(model, {**dict(zip(names, ps)), **buffers}, (xs,))
+            grads = torch.autograd.grad(nn.functional.cross_entropy(pred, ys), ps, allow_unused=True)
+            if accelerated:
+                updates, state = opt.update(list(grads), state, params=ps, inplace=inplace)
+                params = [p.detach().requires_grad_(True) for p in tb.apply_updates(ps, updates, inplace=inplace)]
+            else:
+                new = []
+                for i, (p, g) in enumerate(zip(ps, grads)):
+                    if g is None:
+                        new.append(p)
+                        continue
+                    u, mu[i], nu[i] = plain_scale_by_adam_step(g, mu[i], nu[i], step, 0.9, 0.999, 1e-8, 0.0)
+                    new.append((p + u * (-lr)).detach().requires_grad_(True))
+                params_ref = new
+    assert_close_deltas(params, params_ref, base, dtype)
+
+
+@pytest.mark.parametrize("inner_steps", [2, 3, 5])
+@pytest.mark.parametrize("eps_root,mrg", [(0.0, True), (1e-8, True), (1e-8, False)])
+def test_maml_inner_loop_meta_gradients(inner_steps, eps_root, mrg):
+    """MetaAdam inner loop + outer gradient (reference test_maml_meta_adam, which asserts nothing): the whole-step
+    launch, the chained path and the reference three-node graph must agree bit-for-bit; gradients are finite and the
+    unused parameters get none."""
+    import torchopt_b200 as tb
+    from torchopt_b200 import optim, transform
+    results = []
+    for fuse_step, fused_graph in ((True, True), (False, True), (False, False)):
+        optim.FUSE_STEP, transform.FUSED_GRAPH = fuse_step, fused_graph
+        try:
+            model, _, loader = make(torch.float32, zero_inputs=True)
+            meta_params = list(model.parameters())
+            inner = tb.MetaAdam(model, lr=1e-2, eps_root=eps_root, moment_requires_grad=mrg)
+            xs, ys = loader[0]
+            for _ in range(inner_steps):
+                inner.step(nn.functional.cross_entropy(model(xs), ys))
+            outer = nn.functional.cross_entropy(model(loader[1][0]), loader[1][1])
+            grads = torch.autograd.grad(outer, meta_params, allow_unused=True)
+            torch.cuda.synchronize()
+            results.append(grads)
+        finally:
+            optim.FUSE_STEP, transform.FUSED_GRAPH = True, True
+    names = [n for n, _ in Net(batch_norm=False).named_parameters()]
+    for name, a, b, c in zip(names, *results):
+        if "unused" in name:
+            assert a is None and b is None and c is None
+            continue
+        assert torch.isfinite(a).all()
+        assert torch.equal(a, b) and torch.equal(a, c), f"meta-gradient of {name} differs between dispatch paths"

@@ -71,7 +71,13 @@ def flip_sign_and_add_weight_decay(weight_decay: float = 0.0, maximize: bool = F
             if maximize:
                 g = g.neg_() if inplace else g.neg()
             if weight_decay != 0.0:
-                g = g.add_(params[i], alpha=weight_decay) if inplace else g.add(params[i], alpha=weight_decay)
+                if not inplace:
+                    g = g.add_(params[i], alpha=weight_decay) if maximize else g.add(params[i], alpha=weight_decay)
+                else:
+                    # a gradient outside any graph is decayed with the raw parameter values (alias/utils.py:116-121):
+                    # the in-place write must not be recorded by autograd
+                    p = params[i] if g.requires_grad else params[i].data
+                    g = g.add_(p, alpha=weight_decay)
             out.append(g)
         return out, state
 
