@@ -125,31 +125,45 @@ int b200_adam_fused_backward(int dtype, int64_t num_leaves, const void *const *d
                              const int64_t *n, const uint64_t *count, double b1, double b2, double eps_root,
                              void *stream);
 
-/* ---- whole optimizer step: Adam update + scale(step_size) + apply_updates in one launch (F32 / F64) ---------
- * Replaces, for all leaves at once, the chain  scale_by_accelerated_adam -> scale(-lr) -> apply_updates
- * (alias/adam.py:116-137, transform/scale.py:86-105 `g.mul(step_size)`, update.py:78-79 `p.add(u)`):
- *   mu', nu', u as b200_adam_fused_forward ;  us = u * step_size ;  p_out = p + us      (step_size = -lr)
- * u itself is never stored (the backward recomputes it bit-identically from mu', nu'); `us_out` may be NULL, or its
- * entries NULL, when the caller does not need the scaled update tensor.  28 B/element fp32 (32 with us_out). */
+/* ---- whole optimizer step: recipe + Adam update + scale(step_size) + apply_updates in one launch (F32 / F64) -------
+ * Replaces, for all leaves at once, the chains of alias/adam.py:116-137 and alias/adamw.py:140-151 followed by
+ * apply_updates (update.py:78-79):
+ *   g1 = maximize ? -g : g                                  flip_sign (alias/utils.py:133-191)
+ *   g2 = g1 + wd_l2 * p                 [wd_l2 != 0]        L2 weight decay, `adam(weight_decay=)` (alias/utils.py:116-126)
+ *   mu', nu', u = Adam(g2, mu, nu)                          as b200_adam_fused_forward
+ *   u2 = u + wd_decoupled * p           [wd_decoupled != 0] `adamw` (transform/add_decayed_weights.py:237-247)
+ *   us = u2 * step_size                                     scale(-lr) (transform/scale.py:103), step_size = -lr
+ *   p_out = p + us                                          apply_updates
+ * `x.add(y, alpha=a)` is evaluated like ATen does on CUDA: one rounding, fma(a, y, x).  At most one of wd_l2 /
+ * wd_decoupled may be non-zero.  u is never stored (the backward recomputes it bit-identically from mu', nu');
+ * `us_out` may be NULL, or hold NULL entries, when the scaled update tensor is not needed.
+ * 28 B/element fp32 (32 with us_out). */
 int b200_adam_step_forward(int dtype, int64_t num_leaves, const void *const *p, const void *const *g,
                            const void *const *mu, const void *const *nu, void *const *p_out, void *const *mu_out,
                            void *const *nu_out, void *const *us_out, const int64_t *n, const uint64_t *count,
-                           double b1, double b2, double eps, double eps_root, double step_size, void *stream);
+                           double b1, double b2, double eps, double eps_root, double step_size, double wd_l2,
+                           double wd_decoupled, int maximize, void *stream);
 
 /* In-place, non-differentiable variant (Optimizer.step, optim/base.py:99-124): p += us, g <- us, mu <- mu', nu <- nu'. */
 int b200_adam_step_inplace(int dtype, int64_t num_leaves, void *const *p, void *const *g, void *const *mu,
                            void *const *nu, const int64_t *n, const uint64_t *count, double b1, double b2, double eps,
-                           double eps_root, double step_size, void *stream);
+                           double eps_root, double step_size, double wd_l2, double wd_decoupled, int maximize,
+                           void *stream);
 
 /* Backward of b200_adam_step_forward.  Incoming per leaf (each may be NULL): dp = gradient of p_out, dus = gradient of
  * us_out (the array argument itself may be NULL), dmu_ext / dnu_ext = gradients of mu_out / nu_out.
- *   du = (dp + dus) * step_size ; then exactly b200_adam_fused_backward with u recomputed from new_mu, new_nu.
- * The gradient w.r.t. p is dp itself (p_out = p + us) and is not written by this call.  36 B/element fp32. */
+ *   du2 = (dp + dus) * step_size ; then exactly b200_adam_fused_backward with u recomputed from new_mu, new_nu and the
+ *   gradient that entered the moments re-derived as g2 = fma(wd_l2, p, +-g)  (`p` is required only when wd_l2 != 0);
+ *   dg = maximize ? -dg2 : dg2.
+ * Gradient w.r.t. the parameter: without weight decay it is dp itself and nothing is written (pass dp_out = NULL);
+ * with weight decay dp_out[i] = dp + wd * (du2 | dg2) is written when dp_out[i] != NULL (+4 B/element).
+ * 36 B/element fp32. */
 int b200_adam_step_backward(int dtype, int64_t num_leaves, const void *const *dp, const void *const *dus,
                             const void *const *new_mu, const void *const *new_nu, const void *const *g,
                             const void *const *dmu_ext, const void *const *dnu_ext, void *const *dg, void *const *dmu,
-                            void *const *dnu, const int64_t *n, const uint64_t *count, double b1, double b2,
-                            double eps, double eps_root, double step_size, void *stream);
+                            void *const *dnu, const void *const *p, void *const *dp_out, const int64_t *n,
+                            const uint64_t *count, double b1, double b2, double eps, double eps_root, double step_size,
+                            double wd_l2, double wd_decoupled, int maximize, void *stream);
 
 /* ---- host-buffer entry point (what an application holding HOST arrays calls; used for the e2e number) */
 

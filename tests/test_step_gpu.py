@@ -171,3 +171,123 @@ def test_adam_step_none_grads_and_multi_dtype():
     for i in (0, 1):
         m, v, u = tb.AdamOp(eps_root=1e-8, inplace=False)(mu[i], nu[i], g[i], 1)
         assert torch.equal(new_p[i], p[i] + u * (-1e-2)) and torch.equal(new_mu[i], m) and torch.equal(new_nu[i], v)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# weight decay (L2 and decoupled) and maximize folded into the whole-step launch
+# ---------------------------------------------------------------------------------------------------------------
+RECIPES = [dict(weight_decay=1e-2, decoupled=False, maximize=False), dict(weight_decay=1e-2, decoupled=True, maximize=False),
+           dict(weight_decay=0.0, decoupled=False, maximize=True), dict(weight_decay=3e-2, decoupled=False, maximize=True),
+           dict(weight_decay=3e-2, decoupled=True, maximize=True)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("recipe", RECIPES)
+def test_adam_step_recipes_equal_torch_chain(dtype, recipe):
+    """AdamStep (one launch each way) vs the reference's chain evaluated with torch ops on the same GPU:
+    g.neg(), g.add(p, alpha=wd), the Adam operator, u.add(p, alpha=wd), u.mul(-lr), p.add(u) -- outputs and all
+    gradients (w.r.t. params, grads, moments) bit-identical."""
+    import torchopt_b200 as tb
+    lr, er = 2e-3, 1e-8
+    wd, dec, mx = recipe["weight_decay"], recipe["decoupled"], recipe["maximize"]
+    gen = torch.Generator("cuda").manual_seed(3)
+    sizes = [1, 9, 1000, 4097, 33_001]
+
+    def leaves(scale, positive=False):
+        out = []
+        for k in sizes:
+            t = torch.randn(k, device="cuda", dtype=dtype, generator=gen) * scale
+            out.append((t.abs() if positive else t).requires_grad_(True))
+        return out
+
+    p, g, mu, nu = leaves(0.3), leaves(1e-2), leaves(1e-2), leaves(1e-4, positive=True)
+    douts = [[torch.randn(k, device="cuda", dtype=dtype, generator=gen) for k in sizes] for _ in range(3)]
+    with torch.no_grad():
+        for t in g + mu:
+            t[::7] = 0
+
+    def chain():
+        op = tb.AdamOp(eps_root=er, inplace=False)
+        outs = []
+        for i in range(len(sizes)):
+            gi = g[i].neg() if mx else g[i]
+            if wd and not dec:
+                gi = gi.add(p[i], alpha=wd)
+            m2, v2, u = op(mu[i], nu[i], gi, 2)
+            if wd and dec:
+                u = u.add(p[i], alpha=wd)
+            outs.append((p[i].add(u.mul(-lr)), m2, v2))
+        return [list(x) for x in zip(*outs)]
+
+    def fused():
+        step = tb.AdamStep(eps_root=er, step_size=-lr, **recipe)
+        return [list(x) for x in step(p, g, mu, nu, [2] * len(sizes))]
+
+    res = []
+    for fn in (chain, fused):
+        new_p, new_mu, new_nu = fn()
+        total = sum((a * d).sum() for outs, ds in zip((new_p, new_mu, new_nu), douts) for a, d in zip(outs, ds))
+        grads = torch.autograd.grad(total, p + g + mu + nu)
+        torch.cuda.synchronize()
+        res.append(([t.detach() for t in new_p + new_mu + new_nu], grads))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b), "forward outputs differ from the torch chain"
+    names = ["dp"] * len(sizes) + ["dg"] * len(sizes) + ["dmu"] * len(sizes) + ["dnu"] * len(sizes)
+    for name, a, b in zip(names, res[0][1], res[1][1]):
+        assert torch.equal(a, b), f"{name} differs from the torch chain"
+
+
+@pytest.mark.parametrize("cls_name,wd,mx", [("MetaAdam", 1e-2, False), ("MetaAdam", 1e-2, True), ("MetaAdamW", 1e-2, False),
+                                            ("MetaAdamW", 5e-2, True)])
+def test_meta_optimizers_with_weight_decay_fused_equals_chained(cls_name, wd, mx):
+    import torchopt_b200 as tb
+    from torchopt_b200 import optim
+    x = torch.randn(16, 20, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    y = torch.randn(16, 7, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    out = {}
+    for fuse in (True, False):
+        optim.FUSE_STEP = fuse
+        try:
+            net = _mlp()
+            init = list(net.parameters())
+            opt = getattr(tb, cls_name)(net, lr=1e-2, weight_decay=wd, maximize=mx, eps_root=1e-8)
+            for _ in range(3):
+                opt.step(((net(x) - y) ** 2).mean())
+            meta = torch.autograd.grad(((net(x) - y) ** 2).mean(), init)
+            torch.cuda.synchronize()
+            out[fuse] = ([p.detach() for p in opt.params()], meta)
+        finally:
+            optim.FUSE_STEP = True
+    for a, b in zip(out[True][0] + list(out[True][1]), out[False][0] + list(out[False][1])):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("decoupled", [False, True])
+@pytest.mark.parametrize("maximize", [False, True])
+def test_inplace_optimizers_with_weight_decay(decoupled, maximize):
+    """In-place Adam(weight_decay) / AdamW: fused launch == chained path bit-for-bit, and both track torch.optim
+    (fp64, 25x default tolerances on parameter deltas, as the reference's tests/test_optim.py)."""
+    import torchopt_b200 as tb
+    from torchopt_b200 import optim
+    cls, ref_cls = (tb.AdamW, torch.optim.AdamW) if decoupled else (tb.Adam, torch.optim.Adam)
+    res = {}
+    for fuse in (True, False, "torch"):
+        optim.FUSE_STEP = fuse is True
+        try:
+            net = _mlp(torch.float64)
+            base = [p.detach().clone() for p in net.parameters()]
+            opt = (ref_cls(net.parameters(), lr=1e-3, weight_decay=1e-2, maximize=maximize) if fuse == "torch"
+                   else cls(net.parameters(), lr=1e-3, weight_decay=1e-2, maximize=maximize))
+            gen = torch.Generator("cuda").manual_seed(5)
+            for _ in range(5):
+                x = torch.randn(8, 20, device="cuda", dtype=torch.float64, generator=gen)
+                opt.zero_grad()
+                net(x).pow(2).mean().backward()
+                opt.step()
+            torch.cuda.synchronize()
+            res[fuse] = [p.detach() - b for p, b in zip(net.parameters(), base)]
+        finally:
+            optim.FUSE_STEP = True
+    for a, b, c in zip(res[True], res[False], res["torch"]):
+        assert torch.equal(a, b)
+        torch.testing.assert_close(a, c, rtol=2.5e-6, atol=2.5e-6)

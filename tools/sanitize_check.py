@@ -57,6 +57,16 @@ def run(dtype_id, tdt, gdt, sizes, off):
                           P["dnu"], sizes, cnt, B1, B2, EPS, ER, -1e-3, s)
         abi.step_backward(dtype_id, P["du"], P["du"], P["mu2"], P["nu2"], P["g"], none, P["dne"], P["dg"], none,
                           P["dnu"], sizes, cnt, B1, B2, EPS, ER, -1e-3, s)
+        # weight decay (L2 / decoupled) + maximize: extra p read, extra dp write
+        abi.step_forward(dtype_id, P["p"], P["g"], P["mu"], P["nu"], P["p2"], P["mu2"], P["nu2"], None, sizes, cnt, B1,
+                         B2, EPS, ER, -1e-3, s, wd_l2=1e-2, maximize=True)
+        abi.step_backward(dtype_id, P["du"], None, P["mu2"], P["nu2"], P["g"], P["dme"], P["dne"], P["dg"], P["dmu"],
+                          P["dnu"], sizes, cnt, B1, B2, EPS, ER, -1e-3, s, p=P["p"], dp_out=P["p2"], wd_l2=1e-2,
+                          maximize=True)
+        abi.step_backward(dtype_id, P["du"], None, P["mu2"], P["nu2"], P["g"], none, none, P["dg"], P["dmu"],
+                          P["dnu"], sizes, cnt, B1, B2, EPS, ER, -1e-3, s, dp_out=P["p2"], wd_decoupled=1e-2)
+        abi.step_inplace(dtype_id, P["p"], P["g"], P["mu"], P["nu"], sizes, cnt, B1, B2, EPS, ER, -1e-3, s,
+                         wd_decoupled=1e-2)
         abi.step_inplace(dtype_id, P["p"], P["g"], P["mu"], P["nu"], sizes, cnt, B1, B2, EPS, ER, -1e-3, s)
         for i, n in enumerate(sizes):
             if not n:

@@ -15,13 +15,14 @@ from torchopt_b200._native import _C, adam_op
 from torchopt_b200 import abi, accelerated_op, optim, parallel, transform
 from torchopt_b200.accelerated_op import AdamOp, AdamStep
 from torchopt_b200.accelerated_op import is_available as accelerated_op_available
-from torchopt_b200.optim import Adam, FuncAdam, MetaAdam, adam, apply_updates
+from torchopt_b200.optim import (Adam, AdamW, FuncAdam, FuncAdamW, MetaAdam, MetaAdamW, adam, adamw,
+                                 apply_updates)
 from torchopt_b200.transform import GradientTransformation, ScaleByAdamState, scale_by_accelerated_adam
 
 __version__ = "0.1.0"
 
 __all__ = [
     "_C", "adam_op", "abi", "accelerated_op", "optim", "parallel", "transform",
-    "AdamOp", "AdamStep", "accelerated_op_available", "Adam", "FuncAdam", "MetaAdam", "adam", "apply_updates",
+    "AdamOp", "AdamStep", "accelerated_op_available", "Adam", "AdamW", "FuncAdam", "FuncAdamW", "MetaAdam", "MetaAdamW", "adamw", "adam", "apply_updates",
     "GradientTransformation", "ScaleByAdamState", "scale_by_accelerated_adam",
 ]

@@ -39,11 +39,13 @@ SYMBOLS = {
     "b200_adam_fused_backward": (c_int, [c_int, c_int64, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _i64p,
                                          _u64p, c_double, c_double, c_double, c_void_p]),
     "b200_adam_step_forward": (c_int, [c_int, c_int64, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _i64p, _u64p,
-                                       c_double, c_double, c_double, c_double, c_double, c_void_p]),
+                                       c_double, c_double, c_double, c_double, c_double, c_double, c_double, c_int,
+                                       c_void_p]),
     "b200_adam_step_inplace": (c_int, [c_int, c_int64, _vpp, _vpp, _vpp, _vpp, _i64p, _u64p, c_double, c_double,
-                                       c_double, c_double, c_double, c_void_p]),
+                                       c_double, c_double, c_double, c_double, c_double, c_int, c_void_p]),
     "b200_adam_step_backward": (c_int, [c_int, c_int64, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp,
-                                        _i64p, _u64p, c_double, c_double, c_double, c_double, c_double, c_void_p]),
+                                        _vpp, _vpp, _i64p, _u64p, c_double, c_double, c_double, c_double, c_double,
+                                        c_double, c_double, c_int, c_void_p]),
     "b200_adam_host_step_f32": (c_int, [c_void_p] * 12 + [c_int64, c_double, c_double, c_double, c_double, c_uint64,
                                                           c_int64]),
     "b200_adam_host_release": (c_int, []),
@@ -145,29 +147,32 @@ def fused_backward(dtype, du, u, new_mu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n, c
 
 
 def step_forward(dtype, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2, eps, eps_root, step_size,
-                 stream=0):
-    """Adam + scale(step_size) + apply_updates for all leaves in one launch; ``us_out`` may be None."""
+                 stream=0, wd_l2=0.0, wd_decoupled=0.0, maximize=False):
+    """Recipe + Adam + scale(step_size) + apply_updates for all leaves in one launch; ``us_out`` may be None."""
     L = len(n)
     check(load().b200_adam_step_forward(dtype, L, _ptrs(p), _ptrs(g), _ptrs(mu), _ptrs(nu), _ptrs(p_out),
                                         _ptrs(mu_out), _ptrs(nu_out), None if us_out is None else _ptrs(us_out),
                                         _arr(c_int64, n), _arr(c_uint64, count), b1, b2, eps, eps_root, step_size,
-                                        stream), "step_forward")
+                                        wd_l2, wd_decoupled, int(maximize), stream), "step_forward")
 
 
-def step_inplace(dtype, p, g, mu, nu, n, count, b1, b2, eps, eps_root, step_size, stream=0):
+def step_inplace(dtype, p, g, mu, nu, n, count, b1, b2, eps, eps_root, step_size, stream=0, wd_l2=0.0,
+                 wd_decoupled=0.0, maximize=False):
     L = len(n)
     check(load().b200_adam_step_inplace(dtype, L, _ptrs(p), _ptrs(g), _ptrs(mu), _ptrs(nu), _arr(c_int64, n),
-                                        _arr(c_uint64, count), b1, b2, eps, eps_root, step_size, stream),
-          "step_inplace")
+                                        _arr(c_uint64, count), b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled,
+                                        int(maximize), stream), "step_inplace")
 
 
 def step_backward(dtype, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n, count, b1, b2, eps, eps_root,
-                  step_size, stream=0):
+                  step_size, stream=0, p=None, dp_out=None, wd_l2=0.0, wd_decoupled=0.0, maximize=False):
     L = len(n)
     check(load().b200_adam_step_backward(dtype, L, _ptrs(dp), None if dus is None else _ptrs(dus), _ptrs(new_mu),
                                          _ptrs(new_nu), _ptrs(g), _ptrs(dmu_ext), _ptrs(dnu_ext), _ptrs(dg),
-                                         _ptrs(dmu), _ptrs(dnu), _arr(c_int64, n), _arr(c_uint64, count), b1, b2, eps,
-                                         eps_root, step_size, stream), "step_backward")
+                                         _ptrs(dmu), _ptrs(dnu), None if p is None else _ptrs(p),
+                                         None if dp_out is None else _ptrs(dp_out), _arr(c_int64, n),
+                                         _arr(c_uint64, count), b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled,
+                                         int(maximize), stream), "step_backward")
 
 
 class PreparedFused:

@@ -10,7 +10,8 @@ transform/scale.py:86-105 (``g.mul(-lr)``, 1 launch/leaf) -> update.py:78-79 (``
 Results are bit-identical to running ``scale_by_accelerated_adam`` + ``scale(step_size)`` + ``apply_updates`` with
 torch ops: the kernel performs the same rounded fp32/fp64 operations in the same order (``us = u * S``, ``p' = p + us``;
 backward ``du = dp' * S``), and the two gradient accumulations it absorbs have two addends each.
-SURVEY.md section 8f row n1.  Weight decay / ``maximize`` are not folded in: callers fall back to the chained path.
+SURVEY.md section 8f rows n1 and n3: L2 weight decay (``adam``), decoupled weight decay (``adamw``) and ``maximize``
+are folded into the same launch (``x.add(y, alpha=a)`` evaluated as ATen does on CUDA: fma(a, y, x)).
 """
 from __future__ import annotations
 
@@ -23,46 +24,51 @@ from torchopt_b200.accelerated_op.adam_op import count_as_int
 
 
 class AdamStep:  # pylint: disable=too-few-public-methods
-    """``AdamStep(b1, b2, eps, eps_root, step_size)(params, grads, mu, nu, counts) -> (new_params, new_mu, new_nu)``."""
+    """``AdamStep(...)(params, grads, mu, nu, counts) -> (new_params, new_mu, new_nu)`` for a whole recipe:
+    ``adam`` (optional L2 ``weight_decay``), ``adamw`` (``decoupled=True``), optional ``maximize``."""
 
     class Op(torch.autograd.Function):  # pylint: disable=abstract-method
         """Tensor arguments ``p_0.., g_0.., mu_0.., nu_0..``; outputs ``p'_0.., mu'_0.., nu'_0..``."""
 
         @staticmethod
         def forward(ctx: Any, hyper: tuple, counts: tuple, *tensors: torch.Tensor) -> Any:
-            b1, b2, eps, eps_root, step_size = hyper
+            b1, b2, eps, eps_root, step_size, wd_l2, wd_dec, maximize = hyper
             num = len(counts)
             params, grads = tensors[:num], tensors[num:2 * num]
             mus, nus = tensors[2 * num:3 * num], tensors[3 * num:]
             new_p, new_mu, new_nu, _ = adam_op.fused_step(
                 list(params), list(grads), list(mus), list(nus), b1, b2, eps, eps_root, step_size, list(counts),
-                False, False)
+                False, False, wd_l2, wd_dec, maximize)
             ctx.hyper, ctx.counts = hyper, counts
             ctx.set_materialize_grads(False)
-            ctx.save_for_backward(*grads, *new_mu, *new_nu)   # u is recomputed in the backward kernel
+            # u is recomputed in the backward kernel; the raw parameters are needed only to re-derive g + wd*p
+            extra = params if wd_l2 != 0.0 else ()
+            ctx.save_for_backward(*grads, *new_mu, *new_nu, *extra)
             return (*new_p, *new_mu, *new_nu)
 
         @staticmethod
         def backward(ctx: Any, *douts: torch.Tensor | None) -> Any:
-            b1, b2, eps, eps_root, step_size = ctx.hyper
+            b1, b2, eps, eps_root, step_size, wd_l2, wd_dec, maximize = ctx.hyper
             num = len(ctx.counts)
             saved = ctx.saved_tensors
-            grads, new_mu, new_nu = saved[:num], saved[num:2 * num], saved[2 * num:]
+            grads, new_mu, new_nu = saved[:num], saved[num:2 * num], saved[2 * num:3 * num]
+            params = list(saved[3 * num:]) if wd_l2 != 0.0 else [None] * num
             dparams, dmu_ext, dnu_ext = douts[:num], douts[num:2 * num], douts[2 * num:]
             need = ctx.needs_input_grad[2:]
             need_p, need_g = need[:num], need[num:2 * num]
             need_mu, need_nu = need[2 * num:3 * num], need[3 * num:]
-            dg, dmu, dnu = adam_op.fused_step_backward(
+            dg, dmu, dnu, dp = adam_op.fused_step_backward(
                 list(dparams), [None] * num, list(dmu_ext), list(dnu_ext), list(new_mu), list(new_nu), list(grads),
-                list(need_g), list(need_mu), list(need_nu), b1, b2, eps, eps_root, step_size, list(ctx.counts))
-            # p' = p + us  =>  dL/dp = dL/dp' : hand the incoming tensor straight back, no bytes move
-            dp = [d if n else None for d, n in zip(dparams, need_p)]
+                list(need_g), list(need_mu), list(need_nu), b1, b2, eps, eps_root, step_size, list(ctx.counts),
+                params, list(need_p), wd_l2, wd_dec, maximize)
             return (None, None, *dp, *dg, *dmu, *dnu)
 
     # pylint: disable-next=too-many-arguments
     def __init__(self, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, *, eps_root: float = 0.0,
-                 step_size: float = -1e-3, inplace: bool = False) -> None:
-        self.hyper = (b1, b2, eps, eps_root, step_size)
+                 step_size: float = -1e-3, weight_decay: float = 0.0, decoupled: bool = False, maximize: bool = False,
+                 inplace: bool = False) -> None:
+        wd_l2, wd_dec = (0.0, weight_decay) if decoupled else (weight_decay, 0.0)
+        self.hyper = (b1, b2, eps, eps_root, step_size, wd_l2, wd_dec, bool(maximize))
         self.inplace = inplace
 
     def __call__(self, params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor | None],
@@ -77,9 +83,10 @@ class AdamStep:  # pylint: disable=too-few-public-methods
             return new_p, new_mu, new_nu
         host_counts = tuple(count_as_int(counts[i]) for i in live)
         if self.inplace:
-            b1, b2, eps, eps_root, step_size = self.hyper
+            b1, b2, eps, eps_root, step_size, wd_l2, wd_dec, maximize = self.hyper
             adam_op.fused_step([params[i].data for i in live], [grads[i] for i in live], [mus[i] for i in live],
-                               [nus[i] for i in live], b1, b2, eps, eps_root, step_size, list(host_counts), True, False)
+                               [nus[i] for i in live], b1, b2, eps, eps_root, step_size, list(host_counts), True, False,
+                               wd_l2, wd_dec, maximize)
             return new_p, new_mu, new_nu
         k = len(live)
         flat = self.Op.apply(self.hyper, host_counts, *[params[i] for i in live], *[grads[i] for i in live],

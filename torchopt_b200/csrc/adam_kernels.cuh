@@ -42,6 +42,7 @@ struct Math<float> {
   static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
   static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
   static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
   // tail of backward_updates: the reference's literal 0.5 is a double, so (t*0.5*c2e*den) is evaluated in
   // fp64 and rounded to float once (adam_op_impl_cpu.cpp:315-316).
   static __device__ __forceinline__ float dnu_tail(float t, float c2e, float den) {
@@ -56,6 +57,7 @@ struct Math<double> {
   static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
   static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
   static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
   static __device__ __forceinline__ double dnu_tail(double t, double c2e, double den) {
     return __dmul_rn(__dmul_rn(__dmul_rn(t, 0.5), c2e), den);
   }
@@ -405,15 +407,23 @@ struct FusedBwd {
 //           p' = p + us (update.py:78-79: p.add(u)).  Reads p, g, mu, nu (16 B/elem fp32), writes p', mu', nu'
 //           (12 B) and, only if the caller wants the update tensor, us (4 B).  u itself is never stored: the
 //           backward recomputes it from mu', nu' with the identical instruction sequence (same bits).
+// Optional recipe terms, each skipped entirely when its coefficient is zero, like the reference
+// drops the identity transformation (alias/utils.py:86-87, transform/add_decayed_weights.py:206-207):
+//   maximize      g1 = -g                 (alias/utils.py:133-191: g.neg())
+//   L2 decay      g2 = g1 + WD1 * p       (alias/utils.py:116-126: g.add(p, alpha=wd))         -- `adam(weight_decay=)`
+//   decoupled     u2 = u  + WD2 * p       (transform/add_decayed_weights.py:237-247)            -- `adamw`
+// `x.add(y, alpha=a)` on CUDA is ATen's AddFunctor `x + a * y` compiled with FMA contraction, i.e. ONE rounding:
+// fma(a, y, x).  The kernels use the explicit fma so that they match the torch chain bit-for-bit
+// (tests/test_step_gpu.py compares against torch itself).
 // INPLACE:  p, g, mu, nu updated in place (g <- us), for the non-differentiable Optimizer.step path.
 template <typename T, bool INPLACE>
 struct StepFwd {
   using CT = T;
-  static constexpr int NPTR = 8, NGS = 7, NLS = 2;
+  static constexpr int NPTR = 8, NGS = 10, NLS = 2;
   struct Leaf {
     const T *p, *g, *mu, *nu;
     T *p_o, *mu_o, *nu_o, *us_o;
-    CT B1, OMB1, B2, OMB2, ER, EPS, S, C1, C2;
+    CT B1, OMB1, B2, OMB2, ER, EPS, S, WD1, WD2, SGN, C1, C2;
   };
   template <class Tab>
   static __device__ __forceinline__ Leaf leaf(const Tab &t, int l) {
@@ -422,7 +432,7 @@ struct StepFwd {
     L.nu = (const T *)t.ptr[3][l];
     L.p_o = (T *)t.ptr[4][l], L.mu_o = (T *)t.ptr[5][l], L.nu_o = (T *)t.ptr[6][l], L.us_o = (T *)t.ptr[7][l];
     L.B1 = t.gs[0], L.OMB1 = t.gs[1], L.B2 = t.gs[2], L.OMB2 = t.gs[3], L.ER = t.gs[4], L.EPS = t.gs[5];
-    L.S = t.gs[6];
+    L.S = t.gs[6], L.WD1 = t.gs[7], L.WD2 = t.gs[8], L.SGN = t.gs[9];
     L.C1 = t.ls[0][l], L.C2 = t.ls[1][l];
     return L;
   }
@@ -446,12 +456,16 @@ struct StepFwd {
   template <int P>
   static __device__ __forceinline__ void compute(Regs<P> &r, const Leaf &L) {
     using M = Math<CT>;
+    const bool neg = L.SGN < CT(0), l2 = L.WD1 != CT(0), dec = L.WD2 != CT(0);
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      const CT g = r.g.v[k], m = r.mu.v[k], v = r.nu.v[k];
+      const CT p = r.p.v[k], m = r.mu.v[k], v = r.nu.v[k];
+      CT g = neg ? -r.g.v[k] : r.g.v[k];
+      if (l2) g = M::fma(L.WD1, p, g);
       const CT m_out = M::add(M::mul(L.B1, m), M::mul(L.OMB1, g));
       const CT v_out = M::add(M::mul(L.B2, v), M::mul(M::mul(L.OMB2, g), g));
-      const CT u = M::div(M::mul(m_out, L.C1), M::add(M::sqrt(M::add(M::mul(v_out, L.C2), L.ER)), L.EPS));
+      CT u = M::div(M::mul(m_out, L.C1), M::add(M::sqrt(M::add(M::mul(v_out, L.C2), L.ER)), L.EPS));
+      if (dec) u = M::fma(L.WD2, p, u);
       const CT us = M::mul(u, L.S);
       r.mu.v[k] = m_out;
       r.nu.v[k] = v_out;
@@ -476,15 +490,21 @@ struct StepFwd {
 //   u     = recomputed from mu', nu' (bit-identical to the forward's u)
 //   then exactly FusedBwd: backward_updates, two-addend accumulations, backward_mu, backward_nu, dg = dg_mu + dg_nu
 // Reads dp', mu', nu', g, dmu_ext, dnu_ext (24 B/elem fp32) and writes dg, dmu, dnu (12 B).
+// With weight decay the parameter also feeds the update, so its gradient is no longer the pass-through dp':
+//   decoupled: du2 = (dp'+dus)*S ; du = du2 ; dp_wd = du2 * WD2        (AddBackward with alpha: grad * alpha)
+//   L2       : dg1 = dg2 ; dp_wd = dg2 * WD1 ;  maximize: dg = -dg1     (NegBackward)
+//   dp = dp' + dp_wd (two addends) is written to `dp_out` (+4 B/elem).  backward_nu needs the gradient that ENTERED
+//   the moment update, g2 = fma(WD1, p, +-g); it is re-derived from the saved raw g and p (+4 B/elem read, L2 only).
 // MODE as for FusedBwd: BWD_FULL (all three incoming present), BWD_LAST (dp' only), BWD_GENERIC (run-time NULLs).
 template <typename T, int MODE>
 struct StepBwd {
   using CT = T;
-  static constexpr int NPTR = 10, NGS = 7, NLS = 4;
+  static constexpr int NPTR = 12, NGS = 10, NLS = 4;
+  static constexpr int MAXL_BIG = 160;  // 12 pointers + 4 scalars per leaf: 160 leaves keep the table under 32 KB
   struct Leaf {
-    const T *dp, *dus, *m, *v, *g, *dmu_ext, *dnu_ext;
-    T *dg, *dmu, *dnu;
-    CT B1, OMB1, B2, TWO_OMB2, ER, EPS, S, O1, C2E, C1, C2;
+    const T *dp, *dus, *m, *v, *g, *dmu_ext, *dnu_ext, *p;
+    T *dg, *dmu, *dnu, *dp_o;
+    CT B1, OMB1, B2, TWO_OMB2, ER, EPS, S, WD1, WD2, SGN, O1, C2E, C1, C2;
   };
   template <class Tab>
   static __device__ __forceinline__ Leaf leaf(const Tab &t, int l) {
@@ -493,11 +513,15 @@ struct StepBwd {
     L.v = (const T *)t.ptr[3][l], L.g = (const T *)t.ptr[4][l];
     L.dmu_ext = (const T *)t.ptr[5][l], L.dnu_ext = (const T *)t.ptr[6][l];
     L.dg = (T *)t.ptr[7][l], L.dmu = (T *)t.ptr[8][l], L.dnu = (T *)t.ptr[9][l];
+    L.p = (const T *)t.ptr[10][l], L.dp_o = (T *)t.ptr[11][l];
     L.B1 = t.gs[0], L.OMB1 = t.gs[1], L.B2 = t.gs[2], L.TWO_OMB2 = t.gs[3], L.ER = t.gs[4], L.EPS = t.gs[5];
-    L.S = t.gs[6];
+    L.S = t.gs[6], L.WD1 = t.gs[7], L.WD2 = t.gs[8], L.SGN = t.gs[9];
     L.O1 = t.ls[0][l], L.C2E = t.ls[1][l], L.C1 = t.ls[2][l], L.C2 = t.ls[3][l];
     return L;
   }
+  // raw p is read only when the effective gradient g2 = fma(WD1, p, +-g) has to be re-derived for backward_nu
+  static __device__ __forceinline__ bool need_p(const Leaf &L) { return L.WD1 != CT(0) && L.p != nullptr; }
+  static __device__ __forceinline__ bool want_dp(const Leaf &L) { return L.dp_o != nullptr; }
   static __device__ __forceinline__ bool has_dp(const Leaf &L) { return MODE != BWD_GENERIC || L.dp != nullptr; }
   static __device__ __forceinline__ bool has_dus(const Leaf &L) { return MODE == BWD_GENERIC && L.dus != nullptr; }
   static __device__ __forceinline__ bool has_du(const Leaf &L) { return has_dp(L) || has_dus(L); }
@@ -517,11 +541,12 @@ struct StepBwd {
   static __device__ __forceinline__ bool aligned(const Leaf &L) {
     return is_aligned<T, P>(L.dp) && is_aligned<T, P>(L.dus) && is_aligned<T, P>(L.m) && is_aligned<T, P>(L.v) &&
            is_aligned<T, P>(L.g) && is_aligned<T, P>(L.dmu_ext) && is_aligned<T, P>(L.dnu_ext) &&
-           is_aligned<T, P>(L.dg) && is_aligned<T, P>(L.dmu) && is_aligned<T, P>(L.dnu);
+           is_aligned<T, P>(L.dg) && is_aligned<T, P>(L.dmu) && is_aligned<T, P>(L.dnu) && is_aligned<T, P>(L.p) &&
+           is_aligned<T, P>(L.dp_o);
   }
   template <int P>
   struct Regs {
-    Pack<T, P> dp, dus, m, v, g, dme, dne;  // g -> dg, dme -> dmu, dne -> dnu
+    Pack<T, P> dp, dus, m, v, g, dme, dne, p;  // g -> dg, dme -> dmu, dne -> dnu, dp -> dp_out
   };
   template <int P>
   static __device__ __forceinline__ void load(Regs<P> &r, const Leaf &L, long long i) {
@@ -531,7 +556,10 @@ struct StepBwd {
       load_pack<true>(r.m, L.m + i);
       load_pack<true>(r.v, L.v + i);
     }
-    if (need_g(L)) load_pack<true>(r.g, L.g + i);
+    if (need_g(L)) {
+      load_pack<true>(r.g, L.g + i);
+      if (need_p(L)) load_pack<true>(r.p, L.p + i);
+    }
     if (has_dmu_ext(L)) load_pack<true>(r.dme, L.dmu_ext + i);
     if (has_dnu_ext(L)) load_pack<true>(r.dne, L.dnu_ext + i);
   }
@@ -539,13 +567,14 @@ struct StepBwd {
   static __device__ __forceinline__ void compute(Regs<P> &r, const Leaf &L) {
     using M = Math<CT>;
     const bool hdp = has_dp(L), hdus = has_dus(L), hdu = has_du(L), hme = has_dmu_ext(L), hne = has_dnu_ext(L);
-    const bool ng = need_g(L);
+    const bool ng = need_g(L), np = need_p(L), neg = L.SGN < CT(0), l2 = L.WD1 != CT(0), dec = L.WD2 != CT(0);
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      CT dmu_tot = CT(0), dnu_tot = CT(0);
+      CT dmu_tot = CT(0), dnu_tot = CT(0), dp_wd = CT(0);
       if (hdu) {
         const CT dus = (hdp && hdus) ? M::add(r.dp.v[k], r.dus.v[k]) : (hdp ? r.dp.v[k] : r.dus.v[k]);
         const CT du = M::mul(dus, L.S);
+        if (dec) dp_wd = M::mul(du, L.WD2);
         const CT m = r.m.v[k];
         const CT u = M::div(M::mul(m, L.C1), M::add(M::sqrt(M::add(M::mul(r.v.v[k], L.C2), L.ER)), L.EPS));
         CT dm_new = CT(0), dn_new = CT(0);
@@ -564,10 +593,18 @@ struct StepBwd {
       }
       const bool have_m = hdu || hme, have_n = hdu || hne;
       const CT dg_mu = M::mul(L.OMB1, dmu_tot);
-      const CT dg_nu = ng ? M::mul(M::mul(L.TWO_OMB2, r.g.v[k]), dnu_tot) : CT(0);
-      r.g.v[k] = (have_m && have_n) ? M::add(dg_mu, dg_nu) : (have_m ? dg_mu : dg_nu);
+      CT dg_nu = CT(0);
+      if (ng) {
+        CT g = neg ? -r.g.v[k] : r.g.v[k];      // the gradient that entered the moment update in the forward
+        if (np) g = M::fma(L.WD1, r.p.v[k], g);
+        dg_nu = M::mul(M::mul(L.TWO_OMB2, g), dnu_tot);
+      }
+      const CT dg2 = (have_m && have_n) ? M::add(dg_mu, dg_nu) : (have_m ? dg_mu : dg_nu);
+      if (l2) dp_wd = M::mul(dg2, L.WD1);
+      r.g.v[k] = neg ? -dg2 : dg2;
       r.dme.v[k] = have_m ? M::mul(L.B1, dmu_tot) : CT(0);
       r.dne.v[k] = have_n ? M::mul(L.B2, dnu_tot) : CT(0);
+      r.dp.v[k] = hdp ? M::add(r.dp.v[k], dp_wd) : dp_wd;   // only stored when dp_out is requested
     }
   }
   template <int P>
@@ -575,6 +612,7 @@ struct StepBwd {
     if (want_dg(L)) store_pack(L.dg + i, r.g);
     if (want_dmu(L)) store_pack(L.dmu + i, r.dme);
     if (want_dnu(L)) store_pack(L.dnu + i, r.dne);
+    if (want_dp(L)) store_pack(L.dp_o + i, r.dp);
   }
 };
 

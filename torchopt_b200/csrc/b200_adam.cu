@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "adam_kernels.cuh"
 
@@ -167,12 +168,26 @@ static int run_batches(long long num_leaves, long long total_elems, int flags, c
   return launch_table<Op, P, U, BLOCK, MAXL>(tab, di, stream);
 }
 
+// capacity of the largest leaf table: 256 unless the operator declares a smaller MAXL_BIG (32 KB parameter limit)
+template <class Op, class = void>
+struct MaxLeaves {
+  static constexpr int value = 256;
+};
+template <class Op>
+struct MaxLeaves<Op, std::void_t<decltype(Op::MAXL_BIG)>> {
+  static constexpr int value = Op::MAXL_BIG;
+};
+template <class Op>
+constexpr int max_leaves() {
+  return MaxLeaves<Op>::value;
+}
+
 template <class Op, int P, int U, int BLOCK = B200_ADAM_BLOCK, class NextFn>
 static int run_op(long long num_leaves, long long total_elems, int flags, const typename Op::CT *gs, NextFn &&next,
                   cudaStream_t stream) {
   if (num_leaves <= 1) return run_batches<Op, P, U, BLOCK, 1>(num_leaves, total_elems, flags, gs, next, stream);
   if (num_leaves <= 64) return run_batches<Op, P, U, BLOCK, 64>(num_leaves, total_elems, flags, gs, next, stream);
-  return run_batches<Op, P, U, BLOCK, 256>(num_leaves, total_elems, flags, gs, next, stream);
+  return run_batches<Op, P, U, BLOCK, max_leaves<Op>()>(num_leaves, total_elems, flags, gs, next, stream);
 }
 
 // ---- host wrappers that give every Op an `advance` (pointer bump for >2^28-chunk leaves) ------------
@@ -343,7 +358,7 @@ struct StepFwdH : StepFwd<T, INPLACE> {
 template <typename T, int MODE>
 struct StepBwdH : StepBwd<T, MODE> {
   static void advance(void **p, long long k) {
-    for (int a = 0; a < 10; ++a)
+    for (int a = 0; a < 12; ++a)
       if (p[a]) p[a] = (char *)p[a] + (size_t)k * sizeof(T);
   }
 };
@@ -352,10 +367,12 @@ template <typename T, bool INPLACE>
 static int step_forward_impl(int64_t L, const void *const *p, const void *const *g, const void *const *mu,
                              const void *const *nu, void *const *p_out, void *const *mu_out, void *const *nu_out,
                              void *const *us_out, const int64_t *n, const uint64_t *count, double b1, double b2,
-                             double eps, double eps_root, double step_size, cudaStream_t stream) {
+                             double eps, double eps_root, double step_size, double wd_l2, double wd_decoupled,
+                             int maximize, cudaStream_t stream) {
   using Op = StepFwdH<T, INPLACE>;
   const T B1 = (T)b1, B2 = (T)b2;
-  const T gs[7] = {B1, T(1) - B1, B2, T(1) - B2, (T)eps_root, (T)eps, (T)step_size};
+  const T gs[10] = {B1, T(1) - B1, B2, T(1) - B2, (T)eps_root, (T)eps, (T)step_size, (T)wd_l2, (T)wd_decoupled,
+                    maximize ? T(-1) : T(1)};
   long long total = 0;
   for (int64_t i = 0; i < L; ++i) {
     if (n[i] < 0) return B200_ADAM_E_ARG;
@@ -387,16 +404,19 @@ template <typename T, int MODE>
 static int step_backward_mode(int64_t L, const void *const *dp, const void *const *dus, const void *const *new_mu,
                               const void *const *new_nu, const void *const *g, const void *const *dmu_ext,
                               const void *const *dnu_ext, void *const *dg, void *const *dmu, void *const *dnu,
-                              const int64_t *n, const uint64_t *count, double b1, double b2, double eps,
-                              double eps_root, double step_size, long long total, cudaStream_t stream) {
+                              const void *const *p, void *const *dp_out, const int64_t *n, const uint64_t *count,
+                              double b1, double b2, double eps, double eps_root, double step_size, double wd_l2,
+                              double wd_decoupled, int maximize, long long total, cudaStream_t stream) {
   using Op = StepBwdH<T, MODE>;
   const T B1 = (T)b1, B2 = (T)b2;
-  const T gs[7] = {B1, T(1) - B1, B2, T(2) * (T(1) - B2), (T)eps_root, (T)eps, (T)step_size};
+  const T gs[10] = {B1, T(1) - B1, B2, T(2) * (T(1) - B2), (T)eps_root, (T)eps, (T)step_size, (T)wd_l2,
+                    (T)wd_decoupled, maximize ? T(-1) : T(1)};
   uint64_t last_count = ~0ull;
   T o1 = 0, c2e = 0, c1 = 0, c2 = 0;
   auto next = [&](long long i, HostLeaf<Op> &hl) {
     if (n[i] == 0) return false;
-    if (!dg[i] && !dmu[i] && !dnu[i]) return false;
+    void *dpo = dp_out ? dp_out[i] : nullptr;
+    if (!dg[i] && !dmu[i] && !dnu[i] && !dpo) return false;
     if (count[i] != last_count) {
       last_count = count[i];
       o1 = (T)one_minus_pow(b1, last_count);
@@ -404,9 +424,9 @@ static int step_backward_mode(int64_t L, const void *const *dp, const void *cons
       c1 = (T)inv_one_minus_pow(b1, last_count);
       c2 = (T)inv_one_minus_pow(b2, last_count);
     }
-    const void *q[10] = {dp[i], dus ? dus[i] : nullptr, new_mu[i], new_nu[i], g[i], dmu_ext[i], dnu_ext[i],
-                         dg[i], dmu[i], dnu[i]};
-    for (int a = 0; a < 10; ++a) hl.ptr[a] = const_cast<void *>(q[a]);
+    const void *q[12] = {dp[i], dus ? dus[i] : nullptr, new_mu[i], new_nu[i], g[i], dmu_ext[i], dnu_ext[i],
+                         dg[i], dmu[i], dnu[i], p ? p[i] : nullptr, dpo};
+    for (int a = 0; a < 12; ++a) hl.ptr[a] = const_cast<void *>(q[a]);
     hl.n = n[i];
     hl.ls[0] = o1, hl.ls[1] = c2e, hl.ls[2] = c1, hl.ls[3] = c2;
     return true;
@@ -415,7 +435,9 @@ static int step_backward_mode(int64_t L, const void *const *dp, const void *cons
   if constexpr (MODE == BWD_GENERIC) {
     return run_op<Op, C::P_BWD / 2, 1, 256>(L, total, 0, gs, next, stream);
   } else {
-    return run_op<Op, C::P_BWD, C::U_BWD>(L, total, 0, gs, next, stream);
+    // 256-thread CTAs: the step backward carries one more stream (p) than FusedBwd and would spill under the
+    // 128-register cap of 512-thread CTAs; (P=8, U=2, 256) measured within 0.5 % of (8, 2, 512) in the sweep
+    return run_op<Op, C::P_BWD, C::U_BWD, 256>(L, total, 0, gs, next, stream);
   }
 }
 
@@ -423,8 +445,9 @@ template <typename T>
 static int step_backward_impl(int64_t L, const void *const *dp, const void *const *dus, const void *const *new_mu,
                               const void *const *new_nu, const void *const *g, const void *const *dmu_ext,
                               const void *const *dnu_ext, void *const *dg, void *const *dmu, void *const *dnu,
-                              const int64_t *n, const uint64_t *count, double b1, double b2, double eps,
-                              double eps_root, double step_size, cudaStream_t stream) {
+                              const void *const *p, void *const *dp_out, const int64_t *n, const uint64_t *count,
+                              double b1, double b2, double eps, double eps_root, double step_size, double wd_l2,
+                              double wd_decoupled, int maximize, cudaStream_t stream) {
   bool all_full = true, all_last = true;
   long long total = 0;
   for (int64_t i = 0; i < L; ++i) {
@@ -435,14 +458,15 @@ static int step_backward_impl(int64_t L, const void *const *dp, const void *cons
     const bool hme = dmu_ext[i] != nullptr, hne = dnu_ext[i] != nullptr;
     if ((hdp || hdus) && (!new_mu[i] || !new_nu[i])) return B200_ADAM_E_ARG;
     if (dg[i] && (hdp || hdus || hne) && !g[i]) return B200_ADAM_E_ARG;
+    if (wd_l2 != 0.0 && g[i] && !(p && p[i])) return B200_ADAM_E_ARG;  // L2 decay: g2 is re-derived from g and p
     const bool outs = dg[i] && dmu[i] && dnu[i];
     all_full = all_full && hdp && !hdus && hme && hne && outs;
     all_last = all_last && hdp && !hdus && !hme && !hne && outs;
   }
   if (total == 0) return 0;
 #define B200_STEP_BWD(MODE)                                                                                      \
-  step_backward_mode<T, MODE>(L, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n, count, b1, b2, eps, \
-                              eps_root, step_size, total, stream)
+  step_backward_mode<T, MODE>(L, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, p, dp_out, n, count, b1, \
+                              b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, total, stream)
   if (all_full) return B200_STEP_BWD(BWD_FULL);
   if (all_last) return B200_STEP_BWD(BWD_LAST);
   return B200_STEP_BWD(BWD_GENERIC);
@@ -653,59 +677,64 @@ static int step_forward_dispatch(bool inplace, int dtype, int64_t L, const void 
                                  const void *const *mu, const void *const *nu, void *const *p_out,
                                  void *const *mu_out, void *const *nu_out, void *const *us_out, const int64_t *n,
                                  const uint64_t *count, double b1, double b2, double eps, double eps_root,
-                                 double step_size, void *stream) {
+                                 double step_size, double wd_l2, double wd_decoupled, int maximize, void *stream) {
   if (L < 0) return B200_ADAM_E_ARG;
   if (L == 0) return 0;
   if (!p || !g || !mu || !nu || !p_out || !mu_out || !nu_out || !n || !count) return B200_ADAM_E_ARG;
+  if (wd_l2 != 0.0 && wd_decoupled != 0.0) return B200_ADAM_E_ARG;  // one recipe at a time (adam xor adamw)
   cudaStream_t s = (cudaStream_t)stream;
 #ifndef B200_ADAM_TUNE_F32_ONLY
   if (dtype == B200_ADAM_F64)
     return inplace ? step_forward_impl<double, true>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
-                                                     eps, eps_root, step_size, s)
+                                                     eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s)
                    : step_forward_impl<double, false>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
-                                                      eps, eps_root, step_size, s);
+                                                      eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s);
 #endif
   if (dtype == B200_ADAM_F32)
     return inplace ? step_forward_impl<float, true>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
-                                                    eps, eps_root, step_size, s)
+                                                    eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s)
                    : step_forward_impl<float, false>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
-                                                     eps, eps_root, step_size, s);
+                                                     eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s);
   return B200_ADAM_E_DTYPE;
 }
 
 int b200_adam_step_forward(int dtype, int64_t num_leaves, const void *const *p, const void *const *g,
                            const void *const *mu, const void *const *nu, void *const *p_out, void *const *mu_out,
                            void *const *nu_out, void *const *us_out, const int64_t *n, const uint64_t *count,
-                           double b1, double b2, double eps, double eps_root, double step_size, void *stream) {
+                           double b1, double b2, double eps, double eps_root, double step_size, double wd_l2,
+                           double wd_decoupled, int maximize, void *stream) {
   return step_forward_dispatch(false, dtype, num_leaves, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
-                               eps, eps_root, step_size, stream);
+                               eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, stream);
 }
 
 int b200_adam_step_inplace(int dtype, int64_t num_leaves, void *const *p, void *const *g, void *const *mu,
                            void *const *nu, const int64_t *n, const uint64_t *count, double b1, double b2, double eps,
-                           double eps_root, double step_size, void *stream) {
+                           double eps_root, double step_size, double wd_l2, double wd_decoupled, int maximize,
+                           void *stream) {
   return step_forward_dispatch(true, dtype, num_leaves, p, g, mu, nu, p, mu, nu, g, n, count, b1, b2, eps, eps_root,
-                               step_size, stream);
+                               step_size, wd_l2, wd_decoupled, maximize, stream);
 }
 
 int b200_adam_step_backward(int dtype, int64_t num_leaves, const void *const *dp, const void *const *dus,
                             const void *const *new_mu, const void *const *new_nu, const void *const *g,
                             const void *const *dmu_ext, const void *const *dnu_ext, void *const *dg, void *const *dmu,
-                            void *const *dnu, const int64_t *n, const uint64_t *count, double b1, double b2,
-                            double eps, double eps_root, double step_size, void *stream) {
+                            void *const *dnu, const void *const *p, void *const *dp_out, const int64_t *n,
+                            const uint64_t *count, double b1, double b2, double eps, double eps_root, double step_size,
+                            double wd_l2, double wd_decoupled, int maximize, void *stream) {
   if (num_leaves < 0) return B200_ADAM_E_ARG;
   if (num_leaves == 0) return 0;
   if (!dp || !new_mu || !new_nu || !g || !dmu_ext || !dnu_ext || !dg || !dmu || !dnu || !n || !count)
     return B200_ADAM_E_ARG;
+  if (wd_l2 != 0.0 && wd_decoupled != 0.0) return B200_ADAM_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
 #ifndef B200_ADAM_TUNE_F32_ONLY
   if (dtype == B200_ADAM_F64)
-    return step_backward_impl<double>(num_leaves, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n, count,
-                                      b1, b2, eps, eps_root, step_size, s);
+    return step_backward_impl<double>(num_leaves, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, p, dp_out,
+                                      n, count, b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s);
 #endif
   if (dtype == B200_ADAM_F32)
-    return step_backward_impl<float>(num_leaves, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n, count,
-                                     b1, b2, eps, eps_root, step_size, s);
+    return step_backward_impl<float>(num_leaves, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, p, dp_out,
+                                     n, count, b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s);
   return B200_ADAM_E_DTYPE;
 }
 

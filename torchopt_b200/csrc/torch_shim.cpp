@@ -281,7 +281,8 @@ std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor
 std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>, std::vector<OptTensor>> fused_step(
     const std::vector<Tensor> &params, const std::vector<OptTensor> &grads, const std::vector<Tensor> &mu,
     const std::vector<Tensor> &nu, double b1, double b2, double eps, double eps_root, double step_size,
-    const std::vector<size_t> &count, bool inplace, bool want_updates) {
+    const std::vector<size_t> &count, bool inplace, bool want_updates, double wd_l2, double wd_decoupled,
+    bool maximize) {
   const size_t L = params.size();
   if (grads.size() != L || mu.size() != L || nu.size() != L || count.size() != L)
     throw std::runtime_error("fused_step: params, grads, mu, nu and count must have the same number of leaves");
@@ -322,12 +323,13 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>, std::v
     }
     if (inplace) {
       check(b200_adam_step_inplace(kv.first.dtype, (int64_t)G, op.data(), ous.data(), omu.data(), onu.data(), n.data(),
-                                   cnt.data(), b1, b2, eps, eps_root, step_size, c.stream),
+                                   cnt.data(), b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize ? 1 : 0,
+                                   c.stream),
             "fused_step (inplace)");
     } else {
       check(b200_adam_step_forward(kv.first.dtype, (int64_t)G, pp.data(), pg.data(), pmu.data(), pnu.data(), op.data(),
                                    omu.data(), onu.data(), ous.data(), n.data(), cnt.data(), b1, b2, eps, eps_root,
-                                   step_size, c.stream),
+                                   step_size, wd_l2, wd_decoupled, maximize ? 1 : 0, c.stream),
             "fused_step");
     }
   }
@@ -335,18 +337,23 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>, std::v
 }
 
 // Backward of fused_step: incoming gradients of (new_params, scaled_updates, new_mu, new_nu), saved (new_mu, new_nu,
-// grads).  Returns (dgrads, dmu, dnu); the gradient w.r.t. params is dparams itself and is handled by the caller.
-std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor>> fused_step_backward(
+// grads [, params when wd_l2 != 0]).  Returns (dgrads, dmu, dnu, dparams).  Without weight decay the gradient w.r.t.
+// params is the incoming dparams tensor itself (returned as is, nothing is written); with weight decay it is a new tensor.
+std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor>>
+fused_step_backward(
     const std::vector<OptTensor> &dparams, const std::vector<OptTensor> &dus, const std::vector<OptTensor> &dmu_ext,
     const std::vector<OptTensor> &dnu_ext, const std::vector<Tensor> &new_mu, const std::vector<Tensor> &new_nu,
     const std::vector<Tensor> &g, const std::vector<bool> &need_dg, const std::vector<bool> &need_dmu,
     const std::vector<bool> &need_dnu, double b1, double b2, double eps, double eps_root, double step_size,
-    const std::vector<size_t> &count) {
+    const std::vector<size_t> &count, const std::vector<OptTensor> &params, const std::vector<bool> &need_dp,
+    double wd_l2, double wd_decoupled, bool maximize) {
   const size_t L = g.size();
   if (dparams.size() != L || dus.size() != L || dmu_ext.size() != L || dnu_ext.size() != L || new_mu.size() != L ||
-      new_nu.size() != L || need_dg.size() != L || need_dmu.size() != L || need_dnu.size() != L || count.size() != L)
+      new_nu.size() != L || need_dg.size() != L || need_dmu.size() != L || need_dnu.size() != L || count.size() != L ||
+      params.size() != L || need_dp.size() != L)
     throw std::runtime_error("fused_step_backward: all per-leaf lists must have the same length");
-  std::vector<OptTensor> dg(L), dmu(L), dnu(L);
+  const bool decay = wd_l2 != 0.0 || wd_decoupled != 0.0;
+  std::vector<OptTensor> dg(L), dmu(L), dnu(L), dp(L);
   std::vector<Tensor> cdp(L), cdus(L), cme(L), cne(L);
   std::map<GroupKey, std::vector<size_t>> groups;
   for (size_t i = 0; i < L; ++i) {
@@ -354,9 +361,14 @@ std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor
     const bool hme = dmu_ext[i].has_value(), hne = dnu_ext[i].has_value();
     if (!hdu && !hme && !hne) continue;
     const bool wg = need_dg[i], wm = need_dmu[i] && (hdu || hme), wn = need_dnu[i] && (hdu || hne);
-    if (!wg && !wm && !wn) continue;
+    if (need_dp[i] && !decay) dp[i] = dparams[i];  // p' = p + us: pass-through, no bytes move
+    const bool wp = need_dp[i] && decay;
+    if (!wg && !wm && !wn && !wp) continue;
     require_cuda(g[i]);
     const int dt = family(g[i], new_mu[i], "adamStepBackwardCUDA", false);
+    if (wd_l2 != 0.0 && !params[i].has_value())
+      throw std::runtime_error("fused_step_backward: params are required for L2 weight decay");
+    if (wp) dp[i] = at::empty_like(g[i]);
     if (dparams[i]) cdp[i] = dparams[i]->contiguous(), same_type(cdp[i], g[i]);
     if (dus[i]) cdus[i] = dus[i]->contiguous(), same_type(cdus[i], g[i]);
     if (hme) cme[i] = dmu_ext[i]->contiguous(), same_type(cme[i], g[i]);
@@ -369,8 +381,8 @@ std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor
   for (auto &kv : groups) {
     const auto &idx = kv.second;
     const size_t G = idx.size();
-    std::vector<const void *> pdp(G), pdus(G), pm(G), pv(G), pg(G), pme(G), pne(G);
-    std::vector<void *> odg(G), odm(G), odn(G);
+    std::vector<const void *> pdp(G), pdus(G), pm(G), pv(G), pg(G), pme(G), pne(G), pp(G);
+    std::vector<void *> odg(G), odm(G), odn(G), odp(G);
     std::vector<int64_t> n(G);
     std::vector<uint64_t> cnt(G);
     Ctx c(g[idx[0]]);
@@ -384,14 +396,17 @@ std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor
       odg[k] = dg[i] ? dg[i]->data_ptr() : nullptr;
       odm[k] = dmu[i] ? dmu[i]->data_ptr() : nullptr;
       odn[k] = dnu[i] ? dnu[i]->data_ptr() : nullptr;
+      pp[k] = params[i] ? params[i]->data_ptr() : nullptr;
+      odp[k] = (decay && dp[i]) ? dp[i]->data_ptr() : nullptr;
       n[k] = g[i].numel(), cnt[k] = count[i];
     }
     check(b200_adam_step_backward(kv.first.dtype, (int64_t)G, pdp.data(), pdus.data(), pm.data(), pv.data(), pg.data(),
-                                  pme.data(), pne.data(), odg.data(), odm.data(), odn.data(), n.data(), cnt.data(), b1,
-                                  b2, eps, eps_root, step_size, c.stream),
+                                  pme.data(), pne.data(), odg.data(), odm.data(), odn.data(), pp.data(), odp.data(),
+                                  n.data(), cnt.data(), b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled,
+                                  maximize ? 1 : 0, c.stream),
           "fused_step_backward");
   }
-  return {dg, dmu, dnu};
+  return {dg, dmu, dnu, dp};
 }
 
 // host-buffer step (CPU tensors in, CPU tensors out, work done on the current CUDA device)
@@ -447,11 +462,14 @@ PYBIND11_MODULE(_C, mod) {
   m.def("fused_step", &fused_step, "Adam update + scale(step_size) + apply_updates over all leaves (one launch)",
         py::arg("params"), py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("b1"), py::arg("b2"),
         py::arg("eps"), py::arg("eps_root"), py::arg("step_size"), py::arg("count"), py::arg("inplace") = false,
-        py::arg("want_updates") = false);
+        py::arg("want_updates") = false, py::arg("wd_l2") = 0.0, py::arg("wd_decoupled") = 0.0,
+        py::arg("maximize") = false);
   m.def("fused_step_backward", &fused_step_backward, "Backward of fused_step over all leaves (one launch)",
         py::arg("dparams"), py::arg("dscaled_updates"), py::arg("dmu_ext"), py::arg("dnu_ext"), py::arg("new_mu"),
         py::arg("new_nu"), py::arg("updates"), py::arg("need_dupdates"), py::arg("need_dmu"), py::arg("need_dnu"),
-        py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("step_size"), py::arg("count"));
+        py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("step_size"), py::arg("count"),
+        py::arg("params"), py::arg("need_dparams"), py::arg("wd_l2") = 0.0, py::arg("wd_decoupled") = 0.0,
+        py::arg("maximize") = false);
   m.def("host_step", &host_step, "Fused forward+backward over pinned HOST tensors (pipelined H2D/compute/D2H)",
         py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("dupdates"), py::arg("dmu_ext"), py::arg("dnu_ext"),
         py::arg("out"), py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("count"),

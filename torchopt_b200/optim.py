@@ -102,6 +102,50 @@ def adam(lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999), eps: float
     )
 
 
+def add_decayed_weights(weight_decay: float = 0.0):
+    """``u <- u + wd * p`` (transform/add_decayed_weights.py:195-262, no mask); identity (None) when wd == 0."""
+    if not weight_decay >= 0.0:
+        raise ValueError(f"Invalid weight_decay value: {weight_decay}")
+    if weight_decay == 0.0:
+        return None
+
+    def update_fn(updates: Sequence, state: Any, *, params: Any = None, inplace: bool = True):
+        if params is None:
+            raise ValueError("params are required for weight decay")
+        out = []
+        for p, g in zip(params, updates):
+            if g is None:
+                out.append(None)
+            elif inplace:
+                out.append(g.add_(p if g.requires_grad else p.data, alpha=weight_decay))
+            else:
+                out.append(g.add(p, alpha=weight_decay))
+        return out, state
+
+    return GradientTransformation(lambda params: (), update_fn)
+
+
+# pylint: disable-next=too-many-arguments
+def adamw(lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2, *,
+          eps_root: float = 0.0, mask: Any = None, moment_requires_grad: bool = False, maximize: bool = False,
+          use_accelerated_op: bool = True) -> GradientTransformation:
+    """Functional AdamW over flat leaf lists with the accelerated op (alias/adamw.py:57-151)."""
+    if not use_accelerated_op:
+        raise NotImplementedError("torchopt_b200 only provides the accelerated-op path (use_accelerated_op=True)")
+    if mask is not None:
+        raise NotImplementedError("masked weight decay is outside the scope of torchopt_b200")
+    if not (callable(lr) or lr >= 0.0):
+        raise ValueError(f"Invalid learning rate: {lr}")
+    b1, b2 = betas
+    return chain_flat(
+        flip_sign_and_add_weight_decay(0.0, maximize),
+        scale_by_accelerated_adam.flat(b1=b1, b2=b2, eps=eps, eps_root=eps_root,
+                                       moment_requires_grad=moment_requires_grad),
+        add_decayed_weights(weight_decay),
+        scale(-lr),
+    )
+
+
 def apply_updates(params: Sequence, updates: Sequence, *, inplace: bool = True) -> list:
     """``p + u`` per leaf (update.py:39-81): in place on ``p.data`` or as a new differentiable tensor."""
     out = []
@@ -117,12 +161,13 @@ def apply_updates(params: Sequence, updates: Sequence, *, inplace: bool = True) 
 
 
 def _fused_chain_step(step_op: AdamStep, params: list, grads: list, state: tuple) -> tuple[list, tuple]:
-    """One whole-step launch for the chain (scale_by_accelerated_adam, scale(-lr)) + apply_updates.
-    ``state`` is the chain's state tuple ``(ScaleByAdamState, ())``; the same structure is returned."""
-    adam_state = state[0]
+    """One whole-step launch for a whole adam / adamw chain + apply_updates.  ``state`` is the chain's state tuple
+    (one entry per transformation, exactly one of them a ScaleByAdamState); the same structure is returned."""
+    k = next(i for i, st in enumerate(state) if isinstance(st, ScaleByAdamState))
+    adam_state = state[k]
     count_inc = inc_count_flat(grads, adam_state.count)
     new_params, new_mu, new_nu = step_op(params, grads, adam_state.mu, adam_state.nu, count_inc)
-    return new_params, (ScaleByAdamState(mu=new_mu, nu=new_nu, count=count_inc), *state[1:])
+    return new_params, (*state[:k], ScaleByAdamState(mu=new_mu, nu=new_nu, count=count_inc), *state[k + 1:])
 
 
 class MetaAdam:
@@ -133,15 +178,18 @@ class MetaAdam:
     back-propagate through the whole unroll.
     """
 
+    DECOUPLED = False
+
     # pylint: disable-next=too-many-arguments
     def __init__(self, module: nn.Module, lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 0.0, *, eps_root: float = 0.0,
                  moment_requires_grad: bool = True, maximize: bool = False, use_accelerated_op: bool = True) -> None:
-        self.impl = adam(lr, betas, eps, weight_decay, eps_root=eps_root, moment_requires_grad=moment_requires_grad,
-                         maximize=maximize, use_accelerated_op=use_accelerated_op)
-        # whole-step fusion applies when the chain is exactly [scale_by_accelerated_adam, scale(-lr)]
-        self.fusable = weight_decay == 0.0 and not maximize and not callable(lr)
-        self.step_op = AdamStep(betas[0], betas[1], eps, eps_root=eps_root, step_size=-lr) if self.fusable else None
+        recipe = adamw if self.DECOUPLED else adam
+        self.impl = recipe(lr, betas, eps, weight_decay, eps_root=eps_root, moment_requires_grad=moment_requires_grad,
+                           maximize=maximize, use_accelerated_op=use_accelerated_op)
+        self.fusable = not callable(lr)   # a schedule needs the chained scale_by_schedule, which is out of scope
+        self.step_op = (AdamStep(betas[0], betas[1], eps, eps_root=eps_root, step_size=-lr, weight_decay=weight_decay,
+                                 decoupled=self.DECOUPLED, maximize=maximize) if self.fusable else None)
         self.module = module
         # (owner module, attribute name) for every parameter slot, in named_parameters order
         self.slots = [(m, name) for m in module.modules() for name, p in m._parameters.items() if p is not None]
@@ -173,16 +221,20 @@ class MetaAdam:
 class FuncAdam:
     """Functional Adam over explicit parameter lists (optim/func/base.py:36-120 + optim/func ``FuncAdam``):
     ``new_params = opt.step(loss, params)``.  ``apply_gradients`` is the same step for gradients already at hand.
-    Uses the single whole-step launch when the recipe has no weight decay / maximize."""
+    Uses the single whole-step launch (weight decay and maximize folded in)."""
+
+    DECOUPLED = False
 
     # pylint: disable-next=too-many-arguments
     def __init__(self, lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, *, eps_root: float = 0.0, moment_requires_grad: bool = False,
                  maximize: bool = False, use_accelerated_op: bool = True) -> None:
-        self.impl = adam(lr, betas, eps, weight_decay, eps_root=eps_root, moment_requires_grad=moment_requires_grad,
-                         maximize=maximize, use_accelerated_op=use_accelerated_op)
-        self.fusable = weight_decay == 0.0 and not maximize and not callable(lr)
-        self.hyper = (betas[0], betas[1], eps, eps_root, -lr)
+        recipe = adamw if self.DECOUPLED else adam
+        self.impl = recipe(lr, betas, eps, weight_decay, eps_root=eps_root, moment_requires_grad=moment_requires_grad,
+                           maximize=maximize, use_accelerated_op=use_accelerated_op)
+        self.fusable = not callable(lr)
+        self.hyper = dict(b1=betas[0], b2=betas[1], eps=eps, eps_root=eps_root, step_size=-lr if self.fusable else 0.0,
+                          weight_decay=weight_decay, decoupled=self.DECOUPLED, maximize=maximize)
         self.state = None
 
     def apply_gradients(self, grads: Sequence, params: Sequence, inplace: bool = False) -> list:
@@ -190,8 +242,7 @@ class FuncAdam:
         if self.state is None:
             self.state = self.impl.init(params)
         if self.fusable and FUSE_STEP:
-            b1, b2, eps, eps_root, step_size = self.hyper
-            op = AdamStep(b1, b2, eps, eps_root=eps_root, step_size=step_size, inplace=inplace)
+            op = AdamStep(**self.hyper, inplace=inplace)
             new_params, self.state = _fused_chain_step(op, params, list(grads), self.state)
             return new_params
         updates, self.state = self.impl.update(list(grads), self.state, params=params, inplace=inplace)
@@ -212,16 +263,19 @@ class FuncAdam:
 class Adam:
     """In-place (non-differentiable) Adam over an iterable of parameters (optim/adam.py + optim/base.py:99-124)."""
 
+    DECOUPLED = False
+
     # pylint: disable-next=too-many-arguments
     def __init__(self, params: Iterable[torch.Tensor], lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 0.0, *, eps_root: float = 0.0, maximize: bool = False,
                  use_accelerated_op: bool = True) -> None:
         self.params = list(params)
-        self.impl = adam(lr, betas, eps, weight_decay, eps_root=eps_root, maximize=maximize,
-                         use_accelerated_op=use_accelerated_op)
-        self.fusable = weight_decay == 0.0 and not maximize and not callable(lr)
-        self.step_op = (AdamStep(betas[0], betas[1], eps, eps_root=eps_root, step_size=-lr, inplace=True)
-                        if self.fusable else None)
+        recipe = adamw if self.DECOUPLED else adam
+        self.impl = recipe(lr, betas, eps, weight_decay, eps_root=eps_root, maximize=maximize,
+                           use_accelerated_op=use_accelerated_op)
+        self.fusable = not callable(lr)
+        self.step_op = (AdamStep(betas[0], betas[1], eps, eps_root=eps_root, step_size=-lr, weight_decay=weight_decay,
+                                 decoupled=self.DECOUPLED, maximize=maximize, inplace=True) if self.fusable else None)
         self.state = self.impl.init(self.params)
 
     def zero_grad(self, set_to_none: bool = False) -> None:
@@ -240,3 +294,33 @@ class Adam:
         else:
             updates, self.state = self.impl.update(grads, self.state, params=self.params, inplace=True)
             apply_updates(self.params, updates, inplace=True)
+
+
+class MetaAdamW(MetaAdam):
+    """Differentiable AdamW (optim/meta/adamw.py): decoupled weight decay, default 1e-2."""
+
+    DECOUPLED = True
+
+    def __init__(self, module: nn.Module, lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 1e-2, **kwargs: Any) -> None:
+        super().__init__(module, lr, betas, eps, weight_decay, **kwargs)
+
+
+class FuncAdamW(FuncAdam):
+    """Functional AdamW (optim/func): decoupled weight decay, default 1e-2."""
+
+    DECOUPLED = True
+
+    def __init__(self, lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2, **kwargs: Any) -> None:
+        super().__init__(lr, betas, eps, weight_decay, **kwargs)
+
+
+class AdamW(Adam):
+    """In-place AdamW (optim/adamw.py): decoupled weight decay, default 1e-2."""
+
+    DECOUPLED = True
+
+    def __init__(self, params: Iterable[torch.Tensor], lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 1e-2, **kwargs: Any) -> None:
+        super().__init__(params, lr, betas, eps, weight_decay, **kwargs)
