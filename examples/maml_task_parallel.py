@@ -29,7 +29,7 @@ from torch import nn
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torchopt_b200 as tb  # noqa: E402
-from torchopt_b200.parallel import allreduce_meta_grads, task_slice  # noqa: E402
+from torchopt_b200.parallel import GradBucket, task_slice  # noqa: E402
 
 
 def make_net(n_way: int) -> nn.Module:
@@ -45,6 +45,7 @@ class TaskRunner:
         self.net, self.inner_steps, self.lr = net, inner_steps, lr
         self.slots = [(m, k) for m in net.modules() for k, p in m._parameters.items() if p is not None]
         self.meta_params = [m._parameters[k] for m, k in self.slots]
+        self.bucket = GradBucket(self.meta_params)   # every .grad is a view of ONE flat buffer
 
     def rebind(self):
         for (m, k), p in zip(self.slots, self.meta_params):
@@ -60,8 +61,7 @@ class TaskRunner:
         return loss
 
     def meta_grads(self, data, tasks, num_tasks) -> list:
-        for p in self.meta_params:
-            p.grad = None
+        self.bucket.zero()
         x_spt, y_spt, x_qry, y_qry = data
         for t in tasks:
             (self.query_loss(x_spt[t], y_spt[t], x_qry[t], y_qry[t]) / num_tasks).backward()
@@ -111,7 +111,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         grads = runner.meta_grads(data, mine, T)          # local: sum over my tasks of d(qry_loss / T)
-        allreduce_meta_grads(grads)                        # ONE all-reduce of ONE bucket (75 205 floats)
+        runner.bucket.allreduce()                          # ONE all-reduce, in place on the flat bucket (no copies)
         e1.record()
         torch.cuda.synchronize()
         launches = tb.abi.kernel_launches() - l0

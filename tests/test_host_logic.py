@@ -138,6 +138,24 @@ def _worker(rank: int, world: int, port: int, tmp: str):
         assert out[2] is None
         for a, b in zip(out[:2], want):
             torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-6)
+        # (3) the same through GradBucket: .grad views of one flat buffer, backward accumulates in place,
+        #     the all-reduce runs on the buffer itself
+        from torchopt_b200.parallel import GradBucket
+        torch.manual_seed(1)
+        w = [torch.randn(4, 3, requires_grad=True), torch.randn(6, requires_grad=True)]
+        xs = [torch.randn(3) for _ in range(num_tasks)]
+        bucket = GradBucket(w)
+        bucket.zero()
+        for t in task_slice(num_tasks, rank, world):
+            (((w[0] @ xs[t]).sum() * (t + 1) + (w[1] ** 2).sum() * t) / num_tasks).backward()
+        assert w[0].grad.data_ptr() == bucket.views[0].data_ptr()     # accumulated in place, not replaced
+        bucket.allreduce()
+        ref = [torch.zeros_like(x) for x in w]
+        for t in range(num_tasks):
+            gs = torch.autograd.grad(((w[0] @ xs[t]).sum() * (t + 1) + (w[1] ** 2).sum() * t) / num_tasks, w)
+            ref = [a + b for a, b in zip(ref, gs)]
+        for a, b in zip(w, ref):
+            torch.testing.assert_close(a.grad, b, rtol=1e-5, atol=1e-6)
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -163,3 +181,43 @@ def test_allreduce_meta_grads_single_process():
     out = allreduce_meta_grads(g, scale=0.5)
     assert out[1] is None and torch.equal(out[0], torch.full((3,), 0.5)) and torch.equal(out[2], torch.full((2, 2), 2.0))
     assert allreduce_meta_grads([None]) == [None]
+
+
+def test_zeros_like_flat_matches_zeros_like():
+    """Flat-carved moments have exactly the metadata torch.zeros_like gives (sizes, strides of dense leaves, dtype,
+    leaf-ness, requires_grad) and 128-byte aligned offsets inside their buffer."""
+    from torchopt_b200.transform import zeros_like_flat
+    leaves = [torch.randn(5, 3), None, torch.randn(4, 6).t(), torch.randn(7, dtype=torch.float64), torch.randn(2, 3, 4),
+              torch.randn(2, 2, dtype=torch.float64), torch.randn(2, 3, 4, 5).to(memory_format=torch.channels_last)]
+    for rg in (False, True):
+        out = zeros_like_flat(leaves, requires_grad=rg)
+        base = {}
+        for a, b in zip(leaves, out):
+            if a is None:
+                assert b is None
+                continue
+            r = torch.zeros_like(a)
+            assert b.shape == r.shape and b.stride() == r.stride() and b.dtype == r.dtype
+            assert b.is_leaf and b.requires_grad == rg and bool((b == 0).all())
+            first = base.setdefault(b.dtype, b.data_ptr())
+            assert (b.data_ptr() - first) % 128 == 0
+        if rg:   # independent leaves: a gradient flows into one without touching the others
+            (out[0] * 2).sum().backward()
+            assert out[0].grad is not None and out[2].grad is None
+
+
+def test_grad_bucket_single_process():
+    from torchopt_b200.parallel import GradBucket
+    w = [torch.randn(3, 2, requires_grad=True), torch.randn(5, requires_grad=True)]
+    bucket = GradBucket(w)
+    (w[0].sum() * 2 + (w[1] * 3).sum()).backward()
+    (w[0].sum() * 2 + (w[1] * 3).sum()).backward()
+    assert torch.equal(w[0].grad, torch.full((3, 2), 4.0)) and torch.equal(w[1].grad, torch.full((5,), 6.0))
+    flat = next(iter(bucket.buffers.values()))
+    assert flat.sum() == 4.0 * 6 + 6.0 * 5              # the views ARE the buffer
+    bucket.allreduce(scale=0.5)
+    assert torch.equal(w[0].grad, torch.full((3, 2), 2.0))
+    for p in w:
+        p.grad = None
+    bucket.zero()
+    assert w[0].grad is bucket.views[0] and float(flat.abs().sum()) == 0.0

@@ -14,6 +14,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 #include <torch/extension.h>
+#include <ATen/ExpandUtils.h>
 
 #include <array>
 #include <map>
@@ -157,6 +158,61 @@ std::array<Tensor, 2> backward_updates(const Tensor &dupdates_in, const Tensor &
   return {dmu_out, dnu_out};
 }
 
+// ---- flat output allocation -------------------------------------------------------
+// The multi-tensor entry points return up to 4 tensors per leaf.  Allocating them one by one costs ~1.4 us of
+// caching-allocator work each (186 allocations = ~255 us for a ResNet-18-sized pytree, 4x the kernel time).
+// FlatAlloc hands out every output of a call from ONE buffer per (device, dtype): each output has its donor's sizes
+// and (for dense donors) strides -- exactly what empty_like gives -- and starts on a 128-byte boundary.
+// The outputs are independent tensors sharing a storage (Tensor::set_), not autograd views of each other.
+class FlatAlloc {
+ public:
+  size_t request(const Tensor &donor) {
+    reqs_.push_back(&donor);
+    return reqs_.size() - 1;
+  }
+  void commit() {
+    out_.resize(reqs_.size());
+    if (reqs_.size() <= 3) {  // single-leaf calls: plain empty_like is cheaper than the bookkeeping
+      for (size_t i = 0; i < reqs_.size(); ++i) out_[i] = at::empty_like(*reqs_[i]);
+      return;
+    }
+    struct Group {
+      int64_t total = 0;
+      std::vector<std::pair<size_t, int64_t>> items;  // (request index, element offset)
+    };
+    std::map<std::tuple<int, int, int>, Group> groups;
+    for (size_t i = 0; i < reqs_.size(); ++i) {
+      const Tensor &d = *reqs_[i];
+      const int64_t align = 128 / (int64_t)d.element_size();
+      Group &gr = groups[{(int)d.device().type(), (int)d.device().index(), (int)d.scalar_type()}];
+      gr.total = (gr.total + align - 1) / align * align;
+      gr.items.emplace_back(i, gr.total);
+      gr.total += d.numel();
+    }
+    for (auto &kv : groups) {
+      const Tensor &first = *reqs_[kv.second.items.front().first];
+      Tensor flat = at::empty({kv.second.total}, first.options().memory_format(c10::nullopt));
+      for (auto &it : kv.second.items) {
+        const Tensor &d = *reqs_[it.first];
+        // build the TensorImpl directly (no dispatcher round trips): shares flat's storage, own sizes/strides/offset
+        auto impl = c10::make_intrusive<c10::TensorImpl>(c10::Storage(flat.storage()), flat.key_set(), flat.dtype());
+        impl->set_storage_offset(it.second);
+        if (d.is_non_overlapping_and_dense()) {
+          impl->set_sizes_and_strides(d.sizes(), d.strides());
+        } else {
+          impl->set_sizes_and_strides(d.sizes(), at::infer_dense_strides(d.sizes(), d.strides()));
+        }
+        out_[it.first] = Tensor(std::move(impl));
+      }
+    }
+  }
+  Tensor &operator[](size_t i) { return out_[i]; }
+
+ private:
+  std::vector<const Tensor *> reqs_;
+  std::vector<Tensor> out_;
+};
+
 // ---- fused multi-tensor operators (new) ------------------------------------------------------------
 struct GroupKey {
   int device, dtype;
@@ -193,13 +249,18 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<OptTensor>> fus
     std::vector<int64_t> n(G);
     std::vector<uint64_t> cnt(G);
     Ctx c(*updates[idx[0]]);
+    FlatAlloc fa;
+    if (!inplace) {
+      for (size_t k = 0; k < G; ++k) fa.request(mu[idx[k]]), fa.request(nu[idx[k]]), fa.request(*updates[idx[k]]);
+      fa.commit();
+    }
     for (size_t k = 0; k < G; ++k) {
       const size_t i = idx[k];
       const Tensor &g = *updates[i];
       if (inplace) {
         new_mu[i] = mu[i], new_nu[i] = nu[i], new_u[i] = g;
       } else {
-        new_mu[i] = at::empty_like(mu[i]), new_nu[i] = at::empty_like(nu[i]), new_u[i] = at::empty_like(g);
+        new_mu[i] = fa[3 * k], new_nu[i] = fa[3 * k + 1], new_u[i] = fa[3 * k + 2];
       }
       pg[k] = g.data_ptr(), pmu[k] = mu[i].data_ptr(), pnu[k] = nu[i].data_ptr();
       omu[k] = new_mu[i].data_ptr(), onu[k] = new_nu[i].data_ptr(), ou[k] = new_u[i]->data_ptr();
@@ -231,6 +292,8 @@ std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor
       new_mu.size() != L || need_dg.size() != L || need_dmu.size() != L || need_dnu.size() != L || count.size() != L)
     throw std::runtime_error("fused_backward: all per-leaf lists must have the same length");
   std::vector<OptTensor> dg(L), dmu(L), dnu(L);
+  std::vector<long> slot_dg(L, -1), slot_dmu(L, -1), slot_dnu(L, -1);
+  FlatAlloc fa;
   std::vector<Tensor> cdu(L), cme(L), cne(L);  // keep the .contiguous() copies alive until after the launch
   std::map<GroupKey, std::vector<size_t>> groups;
   for (size_t i = 0; i < L; ++i) {
@@ -243,10 +306,16 @@ std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor
     if (hdu) cdu[i] = dupdates[i]->contiguous(), same_type(cdu[i], g[i]);
     if (hme) cme[i] = dmu_ext[i]->contiguous(), same_type(cme[i], new_mu[i]);
     if (hne) cne[i] = dnu_ext[i]->contiguous(), same_type(cne[i], new_mu[i]);
-    if (wg) dg[i] = at::empty_like(g[i]);
-    if (wm) dmu[i] = at::empty_like(new_mu[i]);
-    if (wn) dnu[i] = at::empty_like(new_mu[i]);
+    if (wg) slot_dg[i] = (long)fa.request(g[i]);
+    if (wm) slot_dmu[i] = (long)fa.request(new_mu[i]);
+    if (wn) slot_dnu[i] = (long)fa.request(new_mu[i]);
     groups[GroupKey{(int)g[i].device().index(), dt}].push_back(i);
+  }
+  fa.commit();
+  for (size_t i = 0; i < L; ++i) {
+    if (slot_dg[i] >= 0) dg[i] = fa[slot_dg[i]];
+    if (slot_dmu[i] >= 0) dmu[i] = fa[slot_dmu[i]];
+    if (slot_dnu[i] >= 0) dnu[i] = fa[slot_dnu[i]];
   }
   for (auto &kv : groups) {
     const auto &idx = kv.second;
@@ -307,14 +376,23 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>, std::v
     std::vector<int64_t> n(G);
     std::vector<uint64_t> cnt(G);
     Ctx c(params[idx[0]]);
+    FlatAlloc fa;
+    const size_t per_leaf = want_updates ? 4 : 3;
+    if (!inplace) {
+      for (size_t k = 0; k < G; ++k) {
+        fa.request(params[idx[k]]), fa.request(mu[idx[k]]), fa.request(nu[idx[k]]);
+        if (want_updates) fa.request(*grads[idx[k]]);
+      }
+      fa.commit();
+    }
     for (size_t k = 0; k < G; ++k) {
       const size_t i = idx[k];
       const Tensor &g = *grads[i];
       if (inplace) {
         new_p[i] = params[i], new_mu[i] = mu[i], new_nu[i] = nu[i], new_us[i] = g;
       } else {
-        new_p[i] = at::empty_like(params[i]), new_mu[i] = at::empty_like(mu[i]), new_nu[i] = at::empty_like(nu[i]);
-        if (want_updates) new_us[i] = at::empty_like(g);
+        new_p[i] = fa[per_leaf * k], new_mu[i] = fa[per_leaf * k + 1], new_nu[i] = fa[per_leaf * k + 2];
+        if (want_updates) new_us[i] = fa[per_leaf * k + 3];
       }
       pp[k] = params[i].data_ptr(), pg[k] = g.data_ptr(), pmu[k] = mu[i].data_ptr(), pnu[k] = nu[i].data_ptr();
       op[k] = new_p[i].data_ptr(), omu[k] = new_mu[i].data_ptr(), onu[k] = new_nu[i].data_ptr();
@@ -354,6 +432,8 @@ fused_step_backward(
     throw std::runtime_error("fused_step_backward: all per-leaf lists must have the same length");
   const bool decay = wd_l2 != 0.0 || wd_decoupled != 0.0;
   std::vector<OptTensor> dg(L), dmu(L), dnu(L), dp(L);
+  std::vector<long> slot_dg(L, -1), slot_dmu(L, -1), slot_dnu(L, -1), slot_dp(L, -1);
+  FlatAlloc fa;
   std::vector<Tensor> cdp(L), cdus(L), cme(L), cne(L);
   std::map<GroupKey, std::vector<size_t>> groups;
   for (size_t i = 0; i < L; ++i) {
@@ -368,15 +448,22 @@ fused_step_backward(
     const int dt = family(g[i], new_mu[i], "adamStepBackwardCUDA", false);
     if (wd_l2 != 0.0 && !params[i].has_value())
       throw std::runtime_error("fused_step_backward: params are required for L2 weight decay");
-    if (wp) dp[i] = at::empty_like(g[i]);
+    if (wp) slot_dp[i] = (long)fa.request(g[i]);
     if (dparams[i]) cdp[i] = dparams[i]->contiguous(), same_type(cdp[i], g[i]);
     if (dus[i]) cdus[i] = dus[i]->contiguous(), same_type(cdus[i], g[i]);
     if (hme) cme[i] = dmu_ext[i]->contiguous(), same_type(cme[i], g[i]);
     if (hne) cne[i] = dnu_ext[i]->contiguous(), same_type(cne[i], g[i]);
-    if (wg) dg[i] = at::empty_like(g[i]);
-    if (wm) dmu[i] = at::empty_like(new_mu[i]);
-    if (wn) dnu[i] = at::empty_like(new_nu[i]);
+    if (wg) slot_dg[i] = (long)fa.request(g[i]);
+    if (wm) slot_dmu[i] = (long)fa.request(new_mu[i]);
+    if (wn) slot_dnu[i] = (long)fa.request(new_nu[i]);
     groups[GroupKey{(int)g[i].device().index(), dt}].push_back(i);
+  }
+  fa.commit();
+  for (size_t i = 0; i < L; ++i) {
+    if (slot_dg[i] >= 0) dg[i] = fa[slot_dg[i]];
+    if (slot_dmu[i] >= 0) dmu[i] = fa[slot_dmu[i]];
+    if (slot_dnu[i] >= 0) dnu[i] = fa[slot_dnu[i]];
+    if (slot_dp[i] >= 0) dp[i] = fa[slot_dp[i]];
   }
   for (auto &kv : groups) {
     const auto &idx = kv.second;

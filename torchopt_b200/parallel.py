@@ -84,3 +84,58 @@ def allreduce_meta_grads(grads: Sequence[torch.Tensor | None], *, scale: float |
         g.copy_(bucket[off:off + k].view_as(g))
         off += k
     return list(grads)
+
+
+class GradBucket:
+    """Flat gradient storage for a parameter list: every ``p.grad`` is a view into ONE buffer per (device, dtype), so
+    the meta-gradient all-reduce needs no flatten / copy-back ("makes the meta-grad all-reduce
+    bucket free").  ``backward()`` accumulates in place into the views (autograd's AccumulateGrad adds into an existing
+    ``.grad``); ``allreduce`` then issues exactly one collective per buffer on the buffer itself.
+
+        bucket = GradBucket(meta_params)
+        bucket.zero()                      # instead of optimizer.zero_grad()
+        ... (loss / num_tasks).backward() for the local tasks ...
+        bucket.allreduce()                 # ONE all_reduce(SUM), in place; .grad views now hold the global gradient
+        meta_optimizer.step()
+    """
+
+    def __init__(self, params: Sequence[torch.Tensor]) -> None:
+        self.params = [p for p in params]
+        self.buffers: dict = {}
+        self.views: list = [None] * len(self.params)
+        groups: dict = {}
+        for i, p in enumerate(self.params):
+            groups.setdefault((p.device, p.dtype), []).append(i)
+        for key, idx in groups.items():
+            align = max(1, 128 // self.params[idx[0]].element_size())
+            offsets, total = [], 0
+            for i in idx:
+                total = (total + align - 1) // align * align
+                offsets.append(total)
+                total += self.params[i].numel()
+            flat = torch.zeros(total, device=key[0], dtype=key[1])
+            self.buffers[key] = flat
+            for i, off in zip(idx, offsets):
+                p = self.params[i]
+                self.views[i] = flat.as_strided(p.shape, p.stride() if p.is_contiguous() else
+                                                torch.empty_like(p).stride(), off)
+        self.attach()
+
+    def attach(self) -> None:
+        """(Re-)install the views as ``.grad`` (needed after ``zero_grad(set_to_none=True)``)."""
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def zero(self) -> None:
+        for flat in self.buffers.values():
+            flat.zero_()
+        self.attach()
+
+    def allreduce(self, *, scale: float | None = None, group: dist.ProcessGroup | None = None) -> None:
+        """In-place SUM over ranks of every flat buffer (one collective each; normally exactly one)."""
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        for flat in self.buffers.values():
+            if scale is not None:
+                flat.mul_(scale)
+            if multi:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)

@@ -48,22 +48,57 @@ def _tag(count: torch.Tensor, host: int) -> torch.Tensor:
 
 
 def make_counts(values: Sequence[int | None], devices: Sequence[torch.device | None]) -> list:
-    """0-dim int64 device tensors holding ``values`` (one host->device copy per device), each tagged with its
-    host mirror.  ``None`` entries stay ``None``."""
+    """0-dim int64 device tensors holding ``values`` (views of ONE vector per device), each tagged with its host
+    mirror.  ``None`` entries stay ``None``.  When all counters of a device agree -- the normal case -- the vector is
+    produced by one fill kernel; otherwise by one small host->device copy."""
     out: list = [None] * len(values)
     by_dev: dict = {}
     for i, (v, d) in enumerate(zip(values, devices)):
         if v is not None:
             by_dev.setdefault(d, []).append(i)
     for dev, idx in by_dev.items():
-        host = torch.tensor([values[i] for i in idx], dtype=torch.int64)
-        if dev.type == "cuda":
-            host = host.pin_memory() if torch.cuda.is_available() else host
-            vec = host.to(dev, non_blocking=True)
+        vals = [values[i] for i in idx]
+        if all(v == vals[0] for v in vals):
+            vec = torch.full((len(idx),), vals[0], dtype=torch.int64, device=dev)
         else:
-            vec = host.to(dev)
-        for j, i in enumerate(idx):
-            out[i] = _tag(vec[j], values[i])
+            host = torch.tensor(vals, dtype=torch.int64)
+            if dev.type == "cuda" and torch.cuda.is_available():
+                vec = host.pin_memory().to(dev, non_blocking=True)
+            else:
+                vec = host.to(dev)
+        for i, view in zip(idx, vec.unbind(0)):
+            out[i] = _tag(view, values[i])
+    return out
+
+
+def zeros_like_flat(leaves: Sequence, requires_grad: bool = False) -> list:
+    """``torch.zeros_like(p, requires_grad=...)`` for every non-None leaf, carved out of ONE zero-filled buffer per
+    (device, dtype): one allocation + one memset instead of one per leaf.  Every result has its
+    leaf's sizes and -- for dense leaves -- strides (what ``zeros_like`` preserves), starts on a 128-byte boundary
+    and is an independent autograd leaf."""
+    out: list = [None] * len(leaves)
+    groups: dict = {}
+    for i, p in enumerate(leaves):
+        if p is not None:
+            groups.setdefault((p.device, p.dtype), []).append(i)
+    for (dev, dtype), idx in groups.items():
+        if len(idx) == 1:
+            out[idx[0]] = torch.zeros_like(leaves[idx[0]], requires_grad=requires_grad)
+            continue
+        align = max(1, 128 // torch.empty((), dtype=dtype).element_size())
+        offsets, total = [], 0
+        for i in idx:
+            total = (total + align - 1) // align * align
+            offsets.append(total)
+            total += leaves[i].numel()
+        flat = torch.zeros(total, dtype=dtype, device=dev)
+        for i, off in zip(idx, offsets):
+            p = leaves[i]
+            # zeros_like keeps the strides of dense leaves (e.g. channels_last / transposed); ask empty_like in the
+            # rare non-contiguous case rather than re-deriving ATen's rule
+            strides = p.stride() if p.is_contiguous() else torch.empty_like(p).stride()
+            t = flat.as_strided(p.shape, strides, off)
+            out[i] = t.requires_grad_(True) if requires_grad else t
     return out
 
 
@@ -100,8 +135,9 @@ def _scale_by_accelerated_adam(b1: float = 0.9, b2: float = 0.999, eps: float = 
         leaves = list(params)
         count = make_counts([None if p is None else 0 for p in leaves],
                             [None if p is None else p.device for p in leaves])
-        mu = [None if p is None else torch.zeros_like(p, requires_grad=moment_requires_grad) for p in leaves]
-        nu = [None if p is None else torch.zeros_like(p, requires_grad=moment_requires_grad) for p in leaves]
+        with torch.no_grad():
+            mu = zeros_like_flat(leaves, requires_grad=moment_requires_grad)
+            nu = zeros_like_flat(leaves, requires_grad=moment_requires_grad)
         return ScaleByAdamState(mu=mu, nu=nu, count=count)
 
     def update_flat(updates: Sequence, state: ScaleByAdamState, inplace: bool):
