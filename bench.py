@@ -277,6 +277,45 @@ def resnet18_unroll(tb, torch, iters: int = 10) -> dict:
                              "note": "scale_by_accelerated_adam launch + torch mul(-lr) + torch add per leaf"}}
 
 
+def whole_step_kernels(abi, torch, n: int = 1 << 28, iters: int = 20) -> dict:
+    """Whole-optimizer-step kernels (Adam + scale(-lr) + apply_updates in one launch each way) through
+    the C ABI on one flat n-element fp32 leaf: forward 28 B/elem (p, g, mu, nu -> p', mu', nu'), backward 36 B/elem
+    (dp', mu', nu', g, dmu_ext, dnu_ext -> dg, dmu, dnu)."""
+    dev = torch.device("cuda")
+    torch.manual_seed(7)
+    t = {k: torch.randn(n, device=dev).mul_(sc) for k, sc in
+         (("p", 0.1), ("g", 1e-2), ("mu", 1e-2), ("dp", 1.0), ("dme", 1e-3), ("dne", 1e-3))}
+    t["nu"] = torch.rand(n, device=dev).mul_(1e-4)
+    o = {k: torch.empty(n, device=dev) for k in ("p2", "mu2", "nu2", "dg", "dmu", "dnu")}
+    P = {k: [v.data_ptr()] for k, v in {**t, **o}.items()}
+    s = torch.cuda.current_stream().cuda_stream
+
+    def fwd():
+        abi.step_forward(abi.F32, P["p"], P["g"], P["mu"], P["nu"], P["p2"], P["mu2"], P["nu2"], None, [n], [COUNT], B1,
+                         B2, EPS, EPS_ROOT, -1e-3, s)
+
+    def bwd():
+        abi.step_backward(abi.F32, P["dp"], None, P["mu2"], P["nu2"], P["g"], P["dme"], P["dne"], P["dg"], P["dmu"],
+                          P["dnu"], [n], [COUNT], B1, B2, EPS, EPS_ROOT, -1e-3, s)
+
+    res = {}
+    for name, fn, nbytes in (("forward", fwd, 28 * n), ("backward", bwd, 36 * n)):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        res[name] = {"ms": ms, "algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9}
+    total_ms = res["forward"]["ms"] + res["backward"]["ms"]
+    res.update(workload=f"whole-step kernels, one flat leaf of {n} fp32 elements (64 B/elem fwd+bwd)",
+               gelem_per_s=n / (total_ms * 1e-3) / 1e9)
+    return res
+
+
 # ---------------------------------------------------------------------------------------------------------
 def run_b200(args) -> None:
     import torch
@@ -389,10 +428,14 @@ def run_b200(args) -> None:
         del prep
         t.clear(), o.clear()
         torch.cuda.empty_cache()
-        try:
-            extra = {"resnet18_unroll5": resnet18_unroll(tb, torch)}
-        except Exception as exc:  # noqa: BLE001  the headline number must survive a failure of the side measurement
-            extra = {"resnet18_unroll5": {"error": repr(exc)}}
+        extra = {}
+        for key, fn in (("resnet18_unroll5", lambda: resnet18_unroll(tb, torch)),
+                        ("whole_step_kernels", lambda: whole_step_kernels(abi, torch))):
+            try:
+                extra[key] = fn()
+            except Exception as exc:  # noqa: BLE001  the headline number must survive a failure of a side measurement
+                extra[key] = {"error": repr(exc)}
+            torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

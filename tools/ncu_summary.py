@@ -62,40 +62,50 @@ def launches(path: str, tag: str, command: str) -> None:
     shutil.copy(path, os.path.join(PROFILES, f"{tag}_launches.csv"))
 
 
-def report(path: str, tag: str, command: str, n_elems: int) -> None:
+def report(path: str, tag: str, command: str, n_elems: int, suffix: str = "") -> None:
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
-    with open(os.path.join(PROFILES, f"{tag}_ncu_full_raw.csv"), "w") as f:
+    with open(os.path.join(PROFILES, f"{tag}_ncu_full{suffix}_raw.csv"), "w") as f:
         f.write(raw)
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
-    out = [f"# {tag}: ncu --set full of the two fused kernels", "", f"Command: `{command}`", "",
+    out = [f"# {tag}: ncu --set full of the two {'whole-step' if suffix else 'fused'} kernels", "", f"Command: `{command}`", "",
            f"n = {n_elems} fp32 elements per array (arrays of 1 GiB >> 126 MB L2).", ""]
-    traffic = {"n_elems": n_elems, "source": f"profiles/{tag}_ncu_full_raw.csv"}
+    traffic = {"n_elems": n_elems, "source": f"profiles/{tag}_ncu_full{suffix}_raw.csv"}
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
         is_bwd = "Bwd" in name
-        alg = (36 if is_bwd else 24) * n_elems
+        per_elem = 36 if is_bwd else (28 if "StepFwd" in name else 24)
+        alg = per_elem * n_elems
         rd = float(r[hdr.index("dram__bytes_read.sum")])
         wr = float(r[hdr.index("dram__bytes_write.sum")])
         u_rd, u_wr = units[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_write.sum")]
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
         tot = rd * scale[u_rd] + wr * scale[u_wr]
-        key = "backward" if is_bwd else "forward"
+        key = ("step_" if "Step" in name else "") + ("backward" if is_bwd else "forward")
         traffic[f"{key}_dram_bytes_per_launch"] = tot
         traffic[f"{key}_dram_bytes_per_elem"] = tot / n_elems
         out += [f"## `{short_name(name)}`", "",
                 f"grid {r[hdr.index('Grid Size')]}, block {r[hdr.index('Block Size')]}; algorithmic bytes "
-                f"{alg / 1e9:.4f} GB ({36 if is_bwd else 24} B/elem); measured DRAM traffic {tot / 1e9:.4f} GB "
+                f"{alg / 1e9:.4f} GB ({per_elem} B/elem); measured DRAM traffic {tot / 1e9:.4f} GB "
                 f"({tot / alg:.3f} x algorithmic).", "", "| metric | value | unit |", "|---|---:|---|"]
         for m in RAW_METRICS:
             if m in hdr:
                 i = hdr.index(m)
                 out.append(f"| `{m}` | {r[i]} | {units[i]} |")
         out.append("")
-    with open(os.path.join(PROFILES, f"{tag}_ncu_full_summary.md"), "w") as f:
+    with open(os.path.join(PROFILES, f"{tag}_ncu_full{suffix}_summary.md"), "w") as f:
         f.write("\n".join(out) + "\n")
-    with open(os.path.join(PROFILES, "ncu_traffic.json"), "w") as f:
-        json.dump(traffic, f, indent=1)
+    tpath = os.path.join(PROFILES, "ncu_traffic.json")
+    merged = {}
+    if os.path.isfile(tpath):
+        merged = json.load(open(tpath))
+    if any(k.startswith("step_") for k in traffic):   # a capture of the step kernels only adds its own keys
+        merged.update({k: v for k, v in traffic.items() if k.startswith("step_")})
+        merged["step_source"] = traffic["source"]
+    else:
+        merged.update(traffic)
+    with open(tpath, "w") as f:
+        json.dump(merged, f, indent=1)
 
 
 if __name__ == "__main__":
@@ -106,9 +116,10 @@ if __name__ == "__main__":
     ap.add_argument("--report")
     ap.add_argument("--report-cmd", default="")
     ap.add_argument("--report-n", type=int, default=1 << 28)
+    ap.add_argument("--suffix", default="", help="e.g. _step for a capture of the whole-step kernels")
     a = ap.parse_args()
     os.makedirs(PROFILES, exist_ok=True)
     if a.launches:
         launches(a.launches, a.round, a.launches_cmd)
     if a.report:
-        report(a.report, a.round, a.report_cmd, a.report_n)
+        report(a.report, a.round, a.report_cmd, a.report_n, a.suffix)

@@ -37,6 +37,12 @@ struct Cfg;  // fwd / bwd / unfused vector configs per dtype family
 #ifndef B200_U_BWD
 #define B200_U_BWD 2
 #endif
+#ifndef B200_STEP_U_BWD
+#define B200_STEP_U_BWD 1
+#endif
+#ifndef B200_STEP_BLOCK_BWD
+#define B200_STEP_BLOCK_BWD 128
+#endif
 template <>
 struct Cfg<float, float> {
   static constexpr int P_FWD = B200_P_FWD, U_FWD = B200_U_FWD, P_BWD = B200_P_BWD, U_BWD = B200_U_BWD, P_UNF = 8,
@@ -435,9 +441,11 @@ static int step_backward_mode(int64_t L, const void *const *dp, const void *cons
   if constexpr (MODE == BWD_GENERIC) {
     return run_op<Op, C::P_BWD / 2, 1, 256>(L, total, 0, gs, next, stream);
   } else {
-    // 256-thread CTAs: the step backward carries one more stream (p) than FusedBwd and would spill under the
-    // 128-register cap of 512-thread CTAs; (P=8, U=2, 256) measured within 0.5 % of (8, 2, 512) in the sweep
-    return run_op<Op, C::P_BWD, C::U_BWD, 256>(L, total, 0, gs, next, stream);
+    // The step backward recomputes u (one more IEEE div + sqrt) and carries one more stream (p) than FusedBwd, so it
+    // is the most instruction-heavy kernel of the family.  Measured (profiles/r01_tune_step.md): U=2 needs 142
+    // registers and halves the resident warps (4.4-4.6 TB/s); U=1 with SMALL CTAs is best -- 128 threads x 92
+    // registers = 5 CTAs (20 warps) per SM, whose compute phases interleave with each other's loads: 7.13 TB/s.
+    return run_op<Op, C::P_BWD, B200_STEP_U_BWD, B200_STEP_BLOCK_BWD>(L, total, 0, gs, next, stream);
   }
 }
 
