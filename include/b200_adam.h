@@ -18,7 +18,8 @@
  *        B200_ADAM_BF16_F32  gradient-side arrays (updates / new_updates / dupdates in and out) are
  *                            bfloat16, moment-side arrays (mu, nu, their grads) are float; arithmetic is
  *                            fp32 on the up-cast inputs with ONE final rounding of bf16 outputs.
- *                            Only the fused / in-place entry points accept it.
+ *                            Accepted by the fused, in-place and whole-step entry points (not by the six
+ *                            out-of-place reference operators).
  *  - Scalars arrive as the reference's pyfloat_t=double / pyuint_t=size_t (include/common.h:23-24).  The
  *    bias corrections are derived on the host exactly as the reference does (std::pow in double, one
  *    rounding to the tensor dtype: adam_op_impl_cuda.cu:73-75,253-255,452-454).
@@ -125,7 +126,7 @@ int b200_adam_fused_backward(int dtype, int64_t num_leaves, const void *const *d
                              const int64_t *n, const uint64_t *count, double b1, double b2, double eps_root,
                              void *stream);
 
-/* ---- whole optimizer step: recipe + Adam update + scale(step_size) + apply_updates in one launch (F32 / F64) -------
+/* ---- whole optimizer step: recipe + Adam update + scale(step_size) + apply_updates in one launch ------------------
  * Replaces, for all leaves at once, the chains of alias/adam.py:116-137 and alias/adamw.py:140-151 followed by
  * apply_updates (update.py:78-79):
  *   g1 = maximize ? -g : g                                  flip_sign (alias/utils.py:133-191)
@@ -134,6 +135,9 @@ int b200_adam_fused_backward(int dtype, int64_t num_leaves, const void *const *d
  *   u2 = u + wd_decoupled * p           [wd_decoupled != 0] `adamw` (transform/add_decayed_weights.py:237-247)
  *   us = u2 * step_size                                     scale(-lr) (transform/scale.py:103), step_size = -lr
  *   p_out = p + us                                          apply_updates
+ * All three dtype families are accepted; with B200_ADAM_BF16_F32 the parameter-side arrays (p, g, us and their
+ * gradients) are bfloat16, the moments float, and every tensor the chain would materialise in bf16 (g2, u, u2, us, p')
+ * is rounded to bf16 at that point, so the result equals the chain evaluated with torch's bf16 ops.
  * `x.add(y, alpha=a)` is evaluated like ATen does on CUDA: one rounding, fma(a, y, x).  At most one of wd_l2 /
  * wd_decoupled may be non-zero.  u is never stored (the backward recomputes it bit-identically from mu', nu');
  * `us_out` may be NULL, or hold NULL entries, when the scaled update tensor is not needed.

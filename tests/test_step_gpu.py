@@ -181,8 +181,11 @@ RECIPES = [dict(weight_decay=1e-2, decoupled=False, maximize=False), dict(weight
            dict(weight_decay=3e-2, decoupled=True, maximize=True)]
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("recipe", RECIPES)
+NO_DECAY = dict(weight_decay=0.0, decoupled=False, maximize=False)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.bfloat16])
+@pytest.mark.parametrize("recipe", RECIPES + [NO_DECAY])
 def test_adam_step_recipes_equal_torch_chain(dtype, recipe):
     """AdamStep (one launch each way) vs the reference's chain evaluated with torch ops on the same GPU:
     g.neg(), g.add(p, alpha=wd), the Adam operator, u.add(p, alpha=wd), u.mul(-lr), p.add(u) -- outputs and all
@@ -193,15 +196,20 @@ def test_adam_step_recipes_equal_torch_chain(dtype, recipe):
     gen = torch.Generator("cuda").manual_seed(3)
     sizes = [1, 9, 1000, 4097, 33_001]
 
-    def leaves(scale, positive=False):
+    # bf16 parameters / gradients keep fp32 moments (the "bf16-param / fp32-state" variant)
+    state_dtype = torch.float32 if dtype is torch.bfloat16 else dtype
+
+    def leaves(scale, positive=False, dt=dtype):
         out = []
         for k in sizes:
-            t = torch.randn(k, device="cuda", dtype=dtype, generator=gen) * scale
-            out.append((t.abs() if positive else t).requires_grad_(True))
+            t = torch.randn(k, device="cuda", dtype=torch.float32, generator=gen) * scale
+            out.append((t.abs() if positive else t).to(dt).requires_grad_(True))
         return out
 
-    p, g, mu, nu = leaves(0.3), leaves(1e-2), leaves(1e-2), leaves(1e-4, positive=True)
-    douts = [[torch.randn(k, device="cuda", dtype=dtype, generator=gen) for k in sizes] for _ in range(3)]
+    p, g = leaves(0.3), leaves(1e-2)
+    mu, nu = leaves(1e-2, dt=state_dtype), leaves(1e-4, positive=True, dt=state_dtype)
+    douts = [[torch.randn(k, device="cuda", dtype=torch.float32, generator=gen).to(dt) for k in sizes]
+             for dt in (dtype, state_dtype, state_dtype)]
     with torch.no_grad():
         for t in g + mu:
             t[::7] = 0
@@ -291,3 +299,31 @@ def test_inplace_optimizers_with_weight_decay(decoupled, maximize):
     for a, b, c in zip(res[True], res[False], res["torch"]):
         assert torch.equal(a, b)
         torch.testing.assert_close(a, c, rtol=2.5e-6, atol=2.5e-6)
+
+
+def test_meta_adam_on_bf16_model_uses_fp32_moments():
+    """A bf16 model through MetaAdam: moments are created in fp32, the whole-step launch handles the mixed family and
+    equals the chained path (fused Adam op + torch's bf16 mul/add) bit-for-bit, parameters and meta-gradients."""
+    import torchopt_b200 as tb
+    from torchopt_b200 import optim
+    x = torch.randn(16, 20, device="cuda", generator=torch.Generator("cuda").manual_seed(1)).bfloat16()
+    y = torch.randn(16, 7, device="cuda", generator=torch.Generator("cuda").manual_seed(2)).bfloat16()
+    out = {}
+    for fuse in (True, False):
+        optim.FUSE_STEP = fuse
+        try:
+            net = _mlp(torch.bfloat16)
+            init = list(net.parameters())
+            opt = tb.MetaAdam(net, lr=1e-2, eps_root=1e-8, weight_decay=1e-2)
+            for _ in range(3):
+                opt.step(((net(x) - y) ** 2).mean())
+            adam_state = next(st for st in opt.state if isinstance(st, tb.ScaleByAdamState))
+            assert all(m.dtype == torch.float32 for m in adam_state.mu + adam_state.nu)
+            assert all(p.dtype == torch.bfloat16 for p in opt.params())
+            meta = torch.autograd.grad(((net(x) - y) ** 2).mean(), init)
+            torch.cuda.synchronize()
+            out[fuse] = [p.detach() for p in opt.params()] + list(meta) + [m.detach() for m in adam_state.mu]
+        finally:
+            optim.FUSE_STEP = True
+    for a, b in zip(out[True], out[False]):
+        assert torch.equal(a, b)

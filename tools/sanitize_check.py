@@ -37,7 +37,7 @@ class Arena:
 
 def run(dtype_id, tdt, gdt, sizes, off):
     s = torch.cuda.current_stream().cuda_stream
-    A = {k: [Arena(n, off, gdt if k in ("g", "du", "u", "dg") else tdt) for n in sizes]
+    A = {k: [Arena(n, off, gdt if k in ("p", "p2", "g", "du", "u", "dg") else tdt) for n in sizes]
          for k in ("p", "g", "mu", "nu", "du", "dme", "dne", "mu2", "nu2", "u", "dg", "dmu", "dnu", "p2")}
     P = {k: [a.ptr() for a in v] for k, v in A.items()}
     cnt = [1 + i % 3 for i in range(len(sizes))]
@@ -50,7 +50,7 @@ def run(dtype_id, tdt, gdt, sizes, off):
     abi.fused_backward(dtype_id, none, P["u"], P["mu2"], P["g"], P["dme"], none, P["dg"], P["dmu"], none, sizes, cnt, B1,
                        B2, ER, s)
     abi.forward_inplace_mt(dtype_id, P["g"], P["mu"], P["nu"], sizes, cnt, B1, B2, EPS, ER, s)
-    if dtype_id != abi.BF16_F32:
+    if True:   # whole-step kernels: all three dtype families
         abi.step_forward(dtype_id, P["p"], P["g"], P["mu"], P["nu"], P["p2"], P["mu2"], P["nu2"], P["u"], sizes, cnt, B1,
                          B2, EPS, ER, -1e-3, s)
         abi.step_backward(dtype_id, P["du"], None, P["mu2"], P["nu2"], P["g"], P["dme"], P["dne"], P["dg"], P["dmu"],
@@ -68,6 +68,7 @@ def run(dtype_id, tdt, gdt, sizes, off):
         abi.step_inplace(dtype_id, P["p"], P["g"], P["mu"], P["nu"], sizes, cnt, B1, B2, EPS, ER, -1e-3, s,
                          wd_decoupled=1e-2)
         abi.step_inplace(dtype_id, P["p"], P["g"], P["mu"], P["nu"], sizes, cnt, B1, B2, EPS, ER, -1e-3, s)
+    if dtype_id != abi.BF16_F32:   # the six out-of-place reference operators: fp32 / fp64 only
         for i, n in enumerate(sizes):
             if not n:
                 continue

@@ -179,6 +179,22 @@ __device__ __forceinline__ void load_pack(Pack<T, P> &r, const T *p) {
   }
 }
 
+// streams that are absent in a launch leave their Pack untouched; zero it so the compiler keeps it in registers
+template <typename T, int P>
+__device__ __forceinline__ void zero_pack(Pack<T, P> &r) {
+#pragma unroll
+  for (int k = 0; k < (int)((sizeof(T) * P + 3) / 4); ++k) r.w[k] = 0u;
+}
+
+template <bool NC, typename T, int P>
+__device__ __forceinline__ void load_or_zero(bool present, Pack<T, P> &r, const T *p) {
+  if (present) {
+    load_pack<NC>(r, p);
+  } else {
+    zero_pack(r);
+  }
+}
+
 template <typename T, int P>
 __device__ __forceinline__ void store_pack(T *p, const Pack<T, P> &r) {
   if constexpr (P == 1) {
@@ -348,14 +364,12 @@ struct FusedBwd {
   };
   template <int P>
   static __device__ __forceinline__ void load(Regs<P> &r, const Leaf &L, long long i) {
-    if (has_du(L)) {
-      load_pack<true>(r.du, L.du + i);
-      load_pack<true>(r.u, L.u + i);
-      load_pack<true>(r.m, L.m + i);
-    }
-    if (need_g(L)) load_pack<true>(r.g, L.g + i);
-    if (has_dmu_ext(L)) load_pack<true>(r.dme, L.dmu_ext + i);
-    if (has_dnu_ext(L)) load_pack<true>(r.dne, L.dnu_ext + i);
+    load_or_zero<true>(has_du(L), r.du, L.du + i);
+    load_or_zero<true>(has_du(L), r.u, L.u + i);
+    load_or_zero<true>(has_du(L), r.m, L.m + i);
+    load_or_zero<true>(need_g(L), r.g, L.g + i);
+    load_or_zero<true>(has_dmu_ext(L), r.dme, L.dmu_ext + i);
+    load_or_zero<true>(has_dnu_ext(L), r.dne, L.dnu_ext + i);
   }
   template <int P>
   static __device__ __forceinline__ void compute(Regs<P> &r, const Leaf &L) {
@@ -416,21 +430,33 @@ struct FusedBwd {
 // fma(a, y, x).  The kernels use the explicit fma so that they match the torch chain bit-for-bit
 // (tests/test_step_gpu.py compares against torch itself).
 // INPLACE:  p, g, mu, nu updated in place (g <- us), for the non-differentiable Optimizer.step path.
-template <typename T, bool INPLACE>
+// Mixed precision (TG = bf16 for p, g, us and their gradients; TS = float moments; CT = float arithmetic): the chain
+// materialises g2, u, u2, us and p' as bf16 TENSORS, so the fused kernel rounds to TG at exactly those points
+// (`rd`); for TG = float / double `rd` is the identity.
+template <typename TG, typename CT>
+__device__ __forceinline__ CT rd(CT x) {
+  return up<CT>(Down<TG, CT>::cvt(x));
+}
+
+template <typename TG_, typename TS_, typename CT_, bool INPLACE>
 struct StepFwd {
-  using CT = T;
+  using TG = TG_;
+  using TS = TS_;
+  using CT = CT_;
   static constexpr int NPTR = 8, NGS = 10, NLS = 2;
   struct Leaf {
-    const T *p, *g, *mu, *nu;
-    T *p_o, *mu_o, *nu_o, *us_o;
+    const TG *p, *g;
+    const TS *mu, *nu;
+    TG *p_o, *us_o;
+    TS *mu_o, *nu_o;
     CT B1, OMB1, B2, OMB2, ER, EPS, S, WD1, WD2, SGN, C1, C2;
   };
   template <class Tab>
   static __device__ __forceinline__ Leaf leaf(const Tab &t, int l) {
     Leaf L;
-    L.p = (const T *)t.ptr[0][l], L.g = (const T *)t.ptr[1][l], L.mu = (const T *)t.ptr[2][l];
-    L.nu = (const T *)t.ptr[3][l];
-    L.p_o = (T *)t.ptr[4][l], L.mu_o = (T *)t.ptr[5][l], L.nu_o = (T *)t.ptr[6][l], L.us_o = (T *)t.ptr[7][l];
+    L.p = (const TG *)t.ptr[0][l], L.g = (const TG *)t.ptr[1][l];
+    L.mu = (const TS *)t.ptr[2][l], L.nu = (const TS *)t.ptr[3][l];
+    L.p_o = (TG *)t.ptr[4][l], L.mu_o = (TS *)t.ptr[5][l], L.nu_o = (TS *)t.ptr[6][l], L.us_o = (TG *)t.ptr[7][l];
     L.B1 = t.gs[0], L.OMB1 = t.gs[1], L.B2 = t.gs[2], L.OMB2 = t.gs[3], L.ER = t.gs[4], L.EPS = t.gs[5];
     L.S = t.gs[6], L.WD1 = t.gs[7], L.WD2 = t.gs[8], L.SGN = t.gs[9];
     L.C1 = t.ls[0][l], L.C2 = t.ls[1][l];
@@ -438,13 +464,14 @@ struct StepFwd {
   }
   template <int P>
   static __device__ __forceinline__ bool aligned(const Leaf &L) {
-    return is_aligned<T, P>(L.p) && is_aligned<T, P>(L.g) && is_aligned<T, P>(L.mu) && is_aligned<T, P>(L.nu) &&
-           is_aligned<T, P>(L.p_o) && is_aligned<T, P>(L.mu_o) && is_aligned<T, P>(L.nu_o) &&
-           is_aligned<T, P>(L.us_o);
+    return is_aligned<TG, P>(L.p) && is_aligned<TG, P>(L.g) && is_aligned<TS, P>(L.mu) && is_aligned<TS, P>(L.nu) &&
+           is_aligned<TG, P>(L.p_o) && is_aligned<TS, P>(L.mu_o) && is_aligned<TS, P>(L.nu_o) &&
+           is_aligned<TG, P>(L.us_o);
   }
   template <int P>
   struct Regs {
-    Pack<T, P> p, g, mu, nu;  // become p', us, mu', nu'
+    Pack<TG, P> p, g;    // become p', us
+    Pack<TS, P> mu, nu;  // become mu', nu'
   };
   template <int P>
   static __device__ __forceinline__ void load(Regs<P> &r, const Leaf &L, long long i) {
@@ -459,18 +486,18 @@ struct StepFwd {
     const bool neg = L.SGN < CT(0), l2 = L.WD1 != CT(0), dec = L.WD2 != CT(0);
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      const CT p = r.p.v[k], m = r.mu.v[k], v = r.nu.v[k];
-      CT g = neg ? -r.g.v[k] : r.g.v[k];
-      if (l2) g = M::fma(L.WD1, p, g);
+      const CT p = up<CT>(r.p.v[k]), m = up<CT>(r.mu.v[k]), v = up<CT>(r.nu.v[k]);
+      CT g = neg ? -up<CT>(r.g.v[k]) : up<CT>(r.g.v[k]);
+      if (l2) g = rd<TG>(M::fma(L.WD1, p, g));
       const CT m_out = M::add(M::mul(L.B1, m), M::mul(L.OMB1, g));
       const CT v_out = M::add(M::mul(L.B2, v), M::mul(M::mul(L.OMB2, g), g));
-      CT u = M::div(M::mul(m_out, L.C1), M::add(M::sqrt(M::add(M::mul(v_out, L.C2), L.ER)), L.EPS));
-      if (dec) u = M::fma(L.WD2, p, u);
-      const CT us = M::mul(u, L.S);
-      r.mu.v[k] = m_out;
-      r.nu.v[k] = v_out;
-      r.g.v[k] = us;
-      r.p.v[k] = M::add(r.p.v[k], us);
+      CT u = rd<TG>(M::div(M::mul(m_out, L.C1), M::add(M::sqrt(M::add(M::mul(v_out, L.C2), L.ER)), L.EPS)));
+      if (dec) u = rd<TG>(M::fma(L.WD2, p, u));
+      const CT us = rd<TG>(M::mul(u, L.S));
+      r.mu.v[k] = Down<TS, CT>::cvt(m_out);
+      r.nu.v[k] = Down<TS, CT>::cvt(v_out);
+      r.g.v[k] = Down<TG, CT>::cvt(us);
+      r.p.v[k] = Down<TG, CT>::cvt(M::add(p, us));
     }
   }
   template <int P>
@@ -496,24 +523,28 @@ struct StepFwd {
 //   dp = dp' + dp_wd (two addends) is written to `dp_out` (+4 B/elem).  backward_nu needs the gradient that ENTERED
 //   the moment update, g2 = fma(WD1, p, +-g); it is re-derived from the saved raw g and p (+4 B/elem read, L2 only).
 // MODE as for FusedBwd: BWD_FULL (all three incoming present), BWD_LAST (dp' only), BWD_GENERIC (run-time NULLs).
-template <typename T, int MODE>
+template <typename TG_, typename TS_, typename CT_, int MODE>
 struct StepBwd {
-  using CT = T;
+  using TG = TG_;
+  using TS = TS_;
+  using CT = CT_;
   static constexpr int NPTR = 12, NGS = 10, NLS = 4;
   static constexpr int MAXL_BIG = 160;  // 12 pointers + 4 scalars per leaf: 160 leaves keep the table under 32 KB
   struct Leaf {
-    const T *dp, *dus, *m, *v, *g, *dmu_ext, *dnu_ext, *p;
-    T *dg, *dmu, *dnu, *dp_o;
+    const TG *dp, *dus, *g, *p;
+    const TS *m, *v, *dmu_ext, *dnu_ext;
+    TG *dg, *dp_o;
+    TS *dmu, *dnu;
     CT B1, OMB1, B2, TWO_OMB2, ER, EPS, S, WD1, WD2, SGN, O1, C2E, C1, C2;
   };
   template <class Tab>
   static __device__ __forceinline__ Leaf leaf(const Tab &t, int l) {
     Leaf L;
-    L.dp = (const T *)t.ptr[0][l], L.dus = (const T *)t.ptr[1][l], L.m = (const T *)t.ptr[2][l];
-    L.v = (const T *)t.ptr[3][l], L.g = (const T *)t.ptr[4][l];
-    L.dmu_ext = (const T *)t.ptr[5][l], L.dnu_ext = (const T *)t.ptr[6][l];
-    L.dg = (T *)t.ptr[7][l], L.dmu = (T *)t.ptr[8][l], L.dnu = (T *)t.ptr[9][l];
-    L.p = (const T *)t.ptr[10][l], L.dp_o = (T *)t.ptr[11][l];
+    L.dp = (const TG *)t.ptr[0][l], L.dus = (const TG *)t.ptr[1][l], L.m = (const TS *)t.ptr[2][l];
+    L.v = (const TS *)t.ptr[3][l], L.g = (const TG *)t.ptr[4][l];
+    L.dmu_ext = (const TS *)t.ptr[5][l], L.dnu_ext = (const TS *)t.ptr[6][l];
+    L.dg = (TG *)t.ptr[7][l], L.dmu = (TS *)t.ptr[8][l], L.dnu = (TS *)t.ptr[9][l];
+    L.p = (const TG *)t.ptr[10][l], L.dp_o = (TG *)t.ptr[11][l];
     L.B1 = t.gs[0], L.OMB1 = t.gs[1], L.B2 = t.gs[2], L.TWO_OMB2 = t.gs[3], L.ER = t.gs[4], L.EPS = t.gs[5];
     L.S = t.gs[6], L.WD1 = t.gs[7], L.WD2 = t.gs[8], L.SGN = t.gs[9];
     L.O1 = t.ls[0][l], L.C2E = t.ls[1][l], L.C1 = t.ls[2][l], L.C2 = t.ls[3][l];
@@ -539,29 +570,26 @@ struct StepBwd {
   }
   template <int P>
   static __device__ __forceinline__ bool aligned(const Leaf &L) {
-    return is_aligned<T, P>(L.dp) && is_aligned<T, P>(L.dus) && is_aligned<T, P>(L.m) && is_aligned<T, P>(L.v) &&
-           is_aligned<T, P>(L.g) && is_aligned<T, P>(L.dmu_ext) && is_aligned<T, P>(L.dnu_ext) &&
-           is_aligned<T, P>(L.dg) && is_aligned<T, P>(L.dmu) && is_aligned<T, P>(L.dnu) && is_aligned<T, P>(L.p) &&
-           is_aligned<T, P>(L.dp_o);
+    return is_aligned<TG, P>(L.dp) && is_aligned<TG, P>(L.dus) && is_aligned<TS, P>(L.m) && is_aligned<TS, P>(L.v) &&
+           is_aligned<TG, P>(L.g) && is_aligned<TS, P>(L.dmu_ext) && is_aligned<TS, P>(L.dnu_ext) &&
+           is_aligned<TG, P>(L.dg) && is_aligned<TS, P>(L.dmu) && is_aligned<TS, P>(L.dnu) && is_aligned<TG, P>(L.p) &&
+           is_aligned<TG, P>(L.dp_o);
   }
   template <int P>
   struct Regs {
-    Pack<T, P> dp, dus, m, v, g, dme, dne, p;  // g -> dg, dme -> dmu, dne -> dnu, dp -> dp_out
+    Pack<TG, P> dp, dus, g, p;      // g -> dg, dp -> dp_out
+    Pack<TS, P> m, v, dme, dne;     // dme -> dmu, dne -> dnu
   };
   template <int P>
   static __device__ __forceinline__ void load(Regs<P> &r, const Leaf &L, long long i) {
-    if (has_dp(L)) load_pack<true>(r.dp, L.dp + i);
-    if (has_dus(L)) load_pack<true>(r.dus, L.dus + i);
-    if (has_du(L)) {
-      load_pack<true>(r.m, L.m + i);
-      load_pack<true>(r.v, L.v + i);
-    }
-    if (need_g(L)) {
-      load_pack<true>(r.g, L.g + i);
-      if (need_p(L)) load_pack<true>(r.p, L.p + i);
-    }
-    if (has_dmu_ext(L)) load_pack<true>(r.dme, L.dmu_ext + i);
-    if (has_dnu_ext(L)) load_pack<true>(r.dne, L.dnu_ext + i);
+    load_or_zero<true>(has_dp(L), r.dp, L.dp + i);
+    load_or_zero<true>(has_dus(L), r.dus, L.dus + i);
+    load_or_zero<true>(has_du(L), r.m, L.m + i);
+    load_or_zero<true>(has_du(L), r.v, L.v + i);
+    load_or_zero<true>(need_g(L), r.g, L.g + i);
+    load_or_zero<true>(need_g(L) && need_p(L), r.p, L.p + i);
+    load_or_zero<true>(has_dmu_ext(L), r.dme, L.dmu_ext + i);
+    load_or_zero<true>(has_dnu_ext(L), r.dne, L.dnu_ext + i);
   }
   template <int P>
   static __device__ __forceinline__ void compute(Regs<P> &r, const Leaf &L) {
@@ -571,12 +599,14 @@ struct StepBwd {
 #pragma unroll
     for (int k = 0; k < P; ++k) {
       CT dmu_tot = CT(0), dnu_tot = CT(0), dp_wd = CT(0);
+      const CT dp_in = hdp ? up<CT>(r.dp.v[k]) : CT(0);
       if (hdu) {
-        const CT dus = (hdp && hdus) ? M::add(r.dp.v[k], r.dus.v[k]) : (hdp ? r.dp.v[k] : r.dus.v[k]);
-        const CT du = M::mul(dus, L.S);
-        if (dec) dp_wd = M::mul(du, L.WD2);
-        const CT m = r.m.v[k];
-        const CT u = M::div(M::mul(m, L.C1), M::add(M::sqrt(M::add(M::mul(r.v.v[k], L.C2), L.ER)), L.EPS));
+        const CT dus = (hdp && hdus) ? rd<TG>(M::add(dp_in, up<CT>(r.dus.v[k]))) : (hdp ? dp_in : up<CT>(r.dus.v[k]));
+        const CT du = rd<TG>(M::mul(dus, L.S));
+        if (dec) dp_wd = rd<TG>(M::mul(du, L.WD2));
+        const CT m = up<CT>(r.m.v[k]);
+        const CT u = rd<TG>(
+            M::div(M::mul(m, L.C1), M::add(M::sqrt(M::add(M::mul(up<CT>(r.v.v[k]), L.C2), L.ER)), L.EPS)));
         CT dm_new = CT(0), dn_new = CT(0);
         if (m != CT(0)) {
           const CT q = M::div(u, m);
@@ -585,26 +615,26 @@ struct StepBwd {
           const CT t = M::mul(M::mul(-du, u), den);
           dn_new = M::dnu_tail(t, L.C2E, den);
         }
-        dmu_tot = hme ? M::add(r.dme.v[k], dm_new) : dm_new;
-        dnu_tot = hne ? M::add(r.dne.v[k], dn_new) : dn_new;
+        dmu_tot = hme ? M::add(up<CT>(r.dme.v[k]), dm_new) : dm_new;
+        dnu_tot = hne ? M::add(up<CT>(r.dne.v[k]), dn_new) : dn_new;
       } else {
-        if (hme) dmu_tot = r.dme.v[k];
-        if (hne) dnu_tot = r.dne.v[k];
+        if (hme) dmu_tot = up<CT>(r.dme.v[k]);
+        if (hne) dnu_tot = up<CT>(r.dne.v[k]);
       }
       const bool have_m = hdu || hme, have_n = hdu || hne;
       const CT dg_mu = M::mul(L.OMB1, dmu_tot);
       CT dg_nu = CT(0);
       if (ng) {
-        CT g = neg ? -r.g.v[k] : r.g.v[k];      // the gradient that entered the moment update in the forward
-        if (np) g = M::fma(L.WD1, r.p.v[k], g);
+        CT g = neg ? -up<CT>(r.g.v[k]) : up<CT>(r.g.v[k]);  // the gradient that entered the moment update
+        if (np) g = rd<TG>(M::fma(L.WD1, up<CT>(r.p.v[k]), g));
         dg_nu = M::mul(M::mul(L.TWO_OMB2, g), dnu_tot);
       }
-      const CT dg2 = (have_m && have_n) ? M::add(dg_mu, dg_nu) : (have_m ? dg_mu : dg_nu);
-      if (l2) dp_wd = M::mul(dg2, L.WD1);
-      r.g.v[k] = neg ? -dg2 : dg2;
-      r.dme.v[k] = have_m ? M::mul(L.B1, dmu_tot) : CT(0);
-      r.dne.v[k] = have_n ? M::mul(L.B2, dnu_tot) : CT(0);
-      r.dp.v[k] = hdp ? M::add(r.dp.v[k], dp_wd) : dp_wd;   // only stored when dp_out is requested
+      const CT dg2 = rd<TG>((have_m && have_n) ? M::add(dg_mu, dg_nu) : (have_m ? dg_mu : dg_nu));
+      if (l2) dp_wd = rd<TG>(M::mul(dg2, L.WD1));
+      r.g.v[k] = Down<TG, CT>::cvt(neg ? -dg2 : dg2);
+      r.dme.v[k] = Down<TS, CT>::cvt(have_m ? M::mul(L.B1, dmu_tot) : CT(0));
+      r.dne.v[k] = Down<TS, CT>::cvt(have_n ? M::mul(L.B2, dnu_tot) : CT(0));
+      r.dp.v[k] = Down<TG, CT>::cvt(hdp ? M::add(dp_in, dp_wd) : dp_wd);  // only stored when dp_out is requested
     }
   }
   template <int P>

@@ -317,8 +317,8 @@ static int fused_backward_mode(int64_t L, const void *const *du, const void *con
   };
   using C = Cfg<TG, TS>;
   if constexpr (MODE == BWD_GENERIC) {
-    // run-time presence flags cost registers: half-width vectors, no unroll, 256-thread CTAs (spill-free)
-    return run_op<Op, C::P_BWD / 2, 1, 256>(L, total, 0, gs, next, stream);
+    // run-time presence flags cost registers: half-width vectors, no unroll, 128-thread CTAs (spill-free)
+    return run_op<Op, C::P_BWD / 2, 1, 128>(L, total, 0, gs, next, stream);
   } else {
     return run_op<Op, C::P_BWD, C::U_BWD>(L, total, 0, gs, next, stream);
   }
@@ -354,28 +354,31 @@ static int fused_backward_impl(int64_t L, const void *const *du, const void *con
 }
 
 // ---- whole-step kernels (Adam + scale(step_size) + apply_updates) ----------------------------------
-template <typename T, bool INPLACE>
-struct StepFwdH : StepFwd<T, INPLACE> {
+template <typename TG, typename TS, typename CT, bool INPLACE>
+struct StepFwdH : StepFwd<TG, TS, CT, INPLACE> {
   static void advance(void **p, long long k) {
+    const size_t sz[8] = {sizeof(TG), sizeof(TG), sizeof(TS), sizeof(TS), sizeof(TG), sizeof(TS), sizeof(TS), sizeof(TG)};
     for (int a = 0; a < 8; ++a)
-      if (p[a]) p[a] = (char *)p[a] + (size_t)k * sizeof(T);
+      if (p[a]) p[a] = (char *)p[a] + (size_t)k * sz[a];
   }
 };
-template <typename T, int MODE>
-struct StepBwdH : StepBwd<T, MODE> {
+template <typename TG, typename TS, typename CT, int MODE>
+struct StepBwdH : StepBwd<TG, TS, CT, MODE> {
   static void advance(void **p, long long k) {
+    const size_t sz[12] = {sizeof(TG), sizeof(TG), sizeof(TS), sizeof(TS), sizeof(TG), sizeof(TS),
+                           sizeof(TS), sizeof(TG), sizeof(TS), sizeof(TS), sizeof(TG), sizeof(TG)};
     for (int a = 0; a < 12; ++a)
-      if (p[a]) p[a] = (char *)p[a] + (size_t)k * sizeof(T);
+      if (p[a]) p[a] = (char *)p[a] + (size_t)k * sz[a];
   }
 };
 
-template <typename T, bool INPLACE>
+template <typename TG, typename TS, typename T, bool INPLACE>
 static int step_forward_impl(int64_t L, const void *const *p, const void *const *g, const void *const *mu,
                              const void *const *nu, void *const *p_out, void *const *mu_out, void *const *nu_out,
                              void *const *us_out, const int64_t *n, const uint64_t *count, double b1, double b2,
                              double eps, double eps_root, double step_size, double wd_l2, double wd_decoupled,
                              int maximize, cudaStream_t stream) {
-  using Op = StepFwdH<T, INPLACE>;
+  using Op = StepFwdH<TG, TS, T, INPLACE>;
   const T B1 = (T)b1, B2 = (T)b2;
   const T gs[10] = {B1, T(1) - B1, B2, T(1) - B2, (T)eps_root, (T)eps, (T)step_size, (T)wd_l2, (T)wd_decoupled,
                     maximize ? T(-1) : T(1)};
@@ -402,18 +405,18 @@ static int step_forward_impl(int64_t L, const void *const *p, const void *const 
     hl.ls[0] = c1, hl.ls[1] = c2;
     return true;
   };
-  using C = Cfg<T, T>;
+  using C = Cfg<TG, TS>;
   return run_op<Op, C::P_FWD, C::U_FWD>(L, total, 0, gs, next, stream);
 }
 
-template <typename T, int MODE>
+template <typename TG, typename TS, typename T, int MODE>
 static int step_backward_mode(int64_t L, const void *const *dp, const void *const *dus, const void *const *new_mu,
                               const void *const *new_nu, const void *const *g, const void *const *dmu_ext,
                               const void *const *dnu_ext, void *const *dg, void *const *dmu, void *const *dnu,
                               const void *const *p, void *const *dp_out, const int64_t *n, const uint64_t *count,
                               double b1, double b2, double eps, double eps_root, double step_size, double wd_l2,
                               double wd_decoupled, int maximize, long long total, cudaStream_t stream) {
-  using Op = StepBwdH<T, MODE>;
+  using Op = StepBwdH<TG, TS, T, MODE>;
   const T B1 = (T)b1, B2 = (T)b2;
   const T gs[10] = {B1, T(1) - B1, B2, T(2) * (T(1) - B2), (T)eps_root, (T)eps, (T)step_size, (T)wd_l2,
                     (T)wd_decoupled, maximize ? T(-1) : T(1)};
@@ -437,9 +440,9 @@ static int step_backward_mode(int64_t L, const void *const *dp, const void *cons
     hl.ls[0] = o1, hl.ls[1] = c2e, hl.ls[2] = c1, hl.ls[3] = c2;
     return true;
   };
-  using C = Cfg<T, T>;
+  using C = Cfg<TG, TS>;
   if constexpr (MODE == BWD_GENERIC) {
-    return run_op<Op, C::P_BWD / 2, 1, 256>(L, total, 0, gs, next, stream);
+    return run_op<Op, C::P_BWD / 2, 1, 128>(L, total, 0, gs, next, stream);
   } else {
     // The step backward recomputes u (one more IEEE div + sqrt) and carries one more stream (p) than FusedBwd, so it
     // is the most instruction-heavy kernel of the family.  Measured (profiles/r01_tune_step.md): U=2 needs 142
@@ -449,7 +452,7 @@ static int step_backward_mode(int64_t L, const void *const *dp, const void *cons
   }
 }
 
-template <typename T>
+template <typename TG, typename TS, typename T>
 static int step_backward_impl(int64_t L, const void *const *dp, const void *const *dus, const void *const *new_mu,
                               const void *const *new_nu, const void *const *g, const void *const *dmu_ext,
                               const void *const *dnu_ext, void *const *dg, void *const *dmu, void *const *dnu,
@@ -473,7 +476,7 @@ static int step_backward_impl(int64_t L, const void *const *dp, const void *cons
   }
   if (total == 0) return 0;
 #define B200_STEP_BWD(MODE)                                                                                      \
-  step_backward_mode<T, MODE>(L, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, p, dp_out, n, count, b1, \
+  step_backward_mode<TG, TS, T, MODE>(L, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, p, dp_out, n, count, b1, \
                               b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, total, stream)
   if (all_full) return B200_STEP_BWD(BWD_FULL);
   if (all_last) return B200_STEP_BWD(BWD_LAST);
@@ -691,18 +694,17 @@ static int step_forward_dispatch(bool inplace, int dtype, int64_t L, const void 
   if (!p || !g || !mu || !nu || !p_out || !mu_out || !nu_out || !n || !count) return B200_ADAM_E_ARG;
   if (wd_l2 != 0.0 && wd_decoupled != 0.0) return B200_ADAM_E_ARG;  // one recipe at a time (adam xor adamw)
   cudaStream_t s = (cudaStream_t)stream;
+#define B200_STEP_FWD(TG, TS, CT)                                                                                   \
+  return inplace ? step_forward_impl<TG, TS, CT, true>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2, \
+                                                       eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s)  \
+                 : step_forward_impl<TG, TS, CT, false>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1,   \
+                                                        b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s)
 #ifndef B200_ADAM_TUNE_F32_ONLY
-  if (dtype == B200_ADAM_F64)
-    return inplace ? step_forward_impl<double, true>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
-                                                     eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s)
-                   : step_forward_impl<double, false>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
-                                                      eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s);
+  if (dtype == B200_ADAM_F64) B200_STEP_FWD(double, double, double);
+  if (dtype == B200_ADAM_BF16_F32) B200_STEP_FWD(bf16_t, float, float);
 #endif
-  if (dtype == B200_ADAM_F32)
-    return inplace ? step_forward_impl<float, true>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
-                                                    eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s)
-                   : step_forward_impl<float, false>(L, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b1, b2,
-                                                     eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s);
+  if (dtype == B200_ADAM_F32) B200_STEP_FWD(float, float, float);
+#undef B200_STEP_FWD
   return B200_ADAM_E_DTYPE;
 }
 
@@ -735,14 +737,16 @@ int b200_adam_step_backward(int dtype, int64_t num_leaves, const void *const *dp
     return B200_ADAM_E_ARG;
   if (wd_l2 != 0.0 && wd_decoupled != 0.0) return B200_ADAM_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+#define B200_STEP_BWD_DT(TG, TS, CT)                                                                                 \
+  return step_backward_impl<TG, TS, CT>(num_leaves, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, p,     \
+                                        dp_out, n, count, b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled,      \
+                                        maximize, s)
 #ifndef B200_ADAM_TUNE_F32_ONLY
-  if (dtype == B200_ADAM_F64)
-    return step_backward_impl<double>(num_leaves, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, p, dp_out,
-                                      n, count, b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s);
+  if (dtype == B200_ADAM_F64) B200_STEP_BWD_DT(double, double, double);
+  if (dtype == B200_ADAM_BF16_F32) B200_STEP_BWD_DT(bf16_t, float, float);
 #endif
-  if (dtype == B200_ADAM_F32)
-    return step_backward_impl<float>(num_leaves, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, p, dp_out,
-                                     n, count, b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s);
+  if (dtype == B200_ADAM_F32) B200_STEP_BWD_DT(float, float, float);
+#undef B200_STEP_BWD_DT
   return B200_ADAM_E_DTYPE;
 }
 

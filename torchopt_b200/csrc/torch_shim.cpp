@@ -344,7 +344,7 @@ std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor
   return {dg, dmu, dnu};
 }
 
-// ---- whole optimizer step: Adam + scale(step_size) + apply_updates (fp32 / fp64) -------------------------
+// ---- whole optimizer step: recipe + Adam + scale(step_size) + apply_updates (fp32 / fp64 / bf16-param+fp32-state) ---
 // Differentiable form: returns (new_params, new_mu, new_nu, scaled_updates?) for leaves whose gradient is not None;
 // leaves without a gradient pass (param, mu, nu, None) through.  `inplace` mutates params/grads/mu/nu instead.
 std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>, std::vector<OptTensor>> fused_step(
@@ -364,8 +364,8 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>, std::v
       continue;
     }
     require_cuda(params[i]);
-    const int dt = family(*grads[i], mu[i], "adamStepCUDA", false);
-    same_type(mu[i], nu[i]), same_type(mu[i], params[i]);
+    const int dt = family(*grads[i], mu[i], "adamStepCUDA", true);
+    same_type(mu[i], nu[i]), same_type(*grads[i], params[i]);
     groups[GroupKey{(int)params[i].device().index(), dt}].push_back(i);
   }
   for (auto &kv : groups) {
@@ -445,14 +445,14 @@ fused_step_backward(
     const bool wp = need_dp[i] && decay;
     if (!wg && !wm && !wn && !wp) continue;
     require_cuda(g[i]);
-    const int dt = family(g[i], new_mu[i], "adamStepBackwardCUDA", false);
+    const int dt = family(g[i], new_mu[i], "adamStepBackwardCUDA", true);
     if (wd_l2 != 0.0 && !params[i].has_value())
       throw std::runtime_error("fused_step_backward: params are required for L2 weight decay");
     if (wp) slot_dp[i] = (long)fa.request(g[i]);
     if (dparams[i]) cdp[i] = dparams[i]->contiguous(), same_type(cdp[i], g[i]);
     if (dus[i]) cdus[i] = dus[i]->contiguous(), same_type(cdus[i], g[i]);
-    if (hme) cme[i] = dmu_ext[i]->contiguous(), same_type(cme[i], g[i]);
-    if (hne) cne[i] = dnu_ext[i]->contiguous(), same_type(cne[i], g[i]);
+    if (hme) cme[i] = dmu_ext[i]->contiguous(), same_type(cme[i], new_mu[i]);
+    if (hne) cne[i] = dnu_ext[i]->contiguous(), same_type(cne[i], new_mu[i]);
     if (wg) slot_dg[i] = (long)fa.request(g[i]);
     if (wm) slot_dmu[i] = (long)fa.request(new_mu[i]);
     if (wn) slot_dnu[i] = (long)fa.request(new_nu[i]);

@@ -42,6 +42,10 @@ class ScaleByAdamState(NamedTuple):
     count: Any
 
 
+# dtype of the Adam moments for a given parameter dtype (identity unless listed)
+STATE_DTYPE = {torch.bfloat16: torch.float32}
+
+
 def _tag(count: torch.Tensor, host: int) -> torch.Tensor:
     count._b200_host_count = host  # type: ignore[attr-defined]
     return count
@@ -71,19 +75,20 @@ def make_counts(values: Sequence[int | None], devices: Sequence[torch.device | N
     return out
 
 
-def zeros_like_flat(leaves: Sequence, requires_grad: bool = False) -> list:
-    """``torch.zeros_like(p, requires_grad=...)`` for every non-None leaf, carved out of ONE zero-filled buffer per
+def zeros_like_flat(leaves: Sequence, requires_grad: bool = False, dtype_map: dict | None = None) -> list:
+    """``torch.zeros_like(p, requires_grad=...)`` (optionally with a remapped dtype) for every non-None leaf, carved out of ONE zero-filled buffer per
     (device, dtype): one allocation + one memset instead of one per leaf.  Every result has its
     leaf's sizes and -- for dense leaves -- strides (what ``zeros_like`` preserves), starts on a 128-byte boundary
     and is an independent autograd leaf."""
     out: list = [None] * len(leaves)
     groups: dict = {}
+    dtype_map = dtype_map or {}
     for i, p in enumerate(leaves):
         if p is not None:
-            groups.setdefault((p.device, p.dtype), []).append(i)
+            groups.setdefault((p.device, dtype_map.get(p.dtype, p.dtype)), []).append(i)
     for (dev, dtype), idx in groups.items():
         if len(idx) == 1:
-            out[idx[0]] = torch.zeros_like(leaves[idx[0]], requires_grad=requires_grad)
+            out[idx[0]] = torch.zeros_like(leaves[idx[0]], dtype=dtype, requires_grad=requires_grad)
             continue
         align = max(1, 128 // torch.empty((), dtype=dtype).element_size())
         offsets, total = [], 0
@@ -135,9 +140,11 @@ def _scale_by_accelerated_adam(b1: float = 0.9, b2: float = 0.999, eps: float = 
         leaves = list(params)
         count = make_counts([None if p is None else 0 for p in leaves],
                             [None if p is None else p.device for p in leaves])
+        # bf16 parameters get fp32 moments (the "bf16-param / fp32-state" variant): the reference would create bf16
+        # moments (zeros_like), in which b2 = 0.999 rounds to 1.0 and nu never accumulates
         with torch.no_grad():
-            mu = zeros_like_flat(leaves, requires_grad=moment_requires_grad)
-            nu = zeros_like_flat(leaves, requires_grad=moment_requires_grad)
+            mu = zeros_like_flat(leaves, requires_grad=moment_requires_grad, dtype_map=STATE_DTYPE)
+            nu = zeros_like_flat(leaves, requires_grad=moment_requires_grad, dtype_map=STATE_DTYPE)
         return ScaleByAdamState(mu=mu, nu=nu, count=count)
 
     def update_flat(updates: Sequence, state: ScaleByAdamState, inplace: bool):
