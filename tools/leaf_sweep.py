@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 B1, B2, EPS, ER, CNT = 0.9, 0.999, 1e-8, 1e-8, 3
+tb_adam_op = None
 RESNET18 = (
     [9408, 64, 64] + [36864, 64, 64] * 4
     + [73728, 128, 128, 147456, 128, 128, 8192, 128, 128] + [147456, 128, 128] * 2
@@ -118,8 +119,11 @@ def main():
     args = ap.parse_args()
     import torch
 
+    import torchopt_b200
     from torchopt_b200 import abi
     abi.load()
+    global tb_adam_op
+    tb_adam_op = torchopt_b200.adam_op
     ref = load_ref_cuda()
     torch.manual_seed(0)
     rows = []
@@ -131,9 +135,15 @@ def main():
             row = {"case": "single leaf", "n": n, "log2n": lg, "dtype": name, "ours_ms": ms,
                    "ours_gelem_s": n / (ms * 1e-3) / 1e9, "ours_gbs": bpe * n / (ms * 1e-3) / 1e9,
                    "fits_l2": 12 * 4 * n < 100e6}
+            if gd == torch.float32:
+                # the same nine calls per leaf through THIS repo's drop-in `_C.adam_op` surface (no Python changes
+                # on the TorchOpt side: INTEGRATION.md section 2 only)
+                dms = reference(torch, tb_adam_op, t, [n])
+                row.update(dropin_surface_ms=dms, dropin_surface_gelem_s=n / (dms * 1e-3) / 1e9)
             if ref is not None and gd == torch.float32:
                 rms = reference(torch, ref, t, [n])
-                row.update(ref_cuda_ms=rms, ref_cuda_gelem_s=n / (rms * 1e-3) / 1e9, speedup=rms / ms)
+                row.update(ref_cuda_ms=rms, ref_cuda_gelem_s=n / (rms * 1e-3) / 1e9, speedup=rms / ms,
+                           dropin_speedup=rms / dms)
             rows.append(row)
             print(json.dumps(row), flush=True)
             del t
@@ -147,9 +157,11 @@ def main():
         row = {"case": label, "n": n, "leaves": len(sizes), "dtype": "fp32", "ours_multi_tensor_ms": ms_mt,
                "ours_multi_tensor_gelem_s": n / (ms_mt * 1e-3) / 1e9, "ours_per_leaf_ms": ms_pl,
                "ours_launches_multi_tensor": 2, "ours_launches_per_leaf": 2 * len(sizes)}
+        dms = reference(torch, tb_adam_op, t, sizes)
+        row.update(dropin_surface_ms=dms)
         if ref is not None:
             rms = reference(torch, ref, t, sizes)
-            row.update(ref_cuda_ms=rms, ref_cuda_launches=9 * len(sizes), speedup=rms / ms_mt)
+            row.update(ref_cuda_ms=rms, ref_cuda_launches=9 * len(sizes), speedup=rms / ms_mt, dropin_speedup=rms / dms)
         rows.append(row)
         print(json.dumps(row), flush=True)
         del t
