@@ -51,7 +51,7 @@ enum b200_adam_error {
   B200_ADAM_OK = 0,
   B200_ADAM_E_DTYPE = -1,    /* dtype not supported by this entry point */
   B200_ADAM_E_ARG = -2,      /* NULL pointer where an array is required, negative size, ... */
-  B200_ADAM_E_NO_DEVICE = -3 /* no CUDA device / not an sm_100 device */
+  B200_ADAM_E_NO_DEVICE = -3 /* the current CUDA device is not compute capability 10.x (B200); no fallback exists */
 };
 
 /* ---- the seven operators of torchopt._C.adam_op (single tensor) -------------------------------- */

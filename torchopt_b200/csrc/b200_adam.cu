@@ -3,14 +3,11 @@
 // Each entry point derives the host scalars exactly like the reference launchers do
 // (/root/reference/src/adam_op/adam_op_impl_cuda.cu:73-75,253-255,452-454 == adam_op_impl_cpu.cpp:72-74,
 // 190-192,327-329: std::pow in double, one rounding to the tensor dtype), fills a leaf table that travels in
-// the kernel parameters and launches ONE persistent streaming kernel (adam_kernels.cuh) on the caller's stream.
+// the kernel parameters and launches ONE streaming kernel (adam_kernels.cuh) on the caller's stream.
 #include "b200_adam.h"
 
 #include <atomic>
 #include <cmath>
-#include <cstdio>
-#include <cstring>
-#include <mutex>
 #include <type_traits>
 
 #include "adam_kernels.cuh"
@@ -83,6 +80,8 @@ static int device_info(DeviceInfo *out) {
     ready[dev].store(1, std::memory_order_release);
   }
   *out = cache[dev];
+  // the library carries sm_100a SASS only: fail with a clear code instead of "no kernel image" on anything else
+  if (out->cc_major != 10) return B200_ADAM_E_NO_DEVICE;
   return 0;
 }
 
@@ -545,7 +544,7 @@ const char *b200_adam_error_string(int code) {
     case B200_ADAM_OK: return "ok";
     case B200_ADAM_E_DTYPE: return "b200_adam: dtype not supported by this entry point";
     case B200_ADAM_E_ARG: return "b200_adam: invalid argument (NULL array, negative size or missing saved tensor)";
-    case B200_ADAM_E_NO_DEVICE: return "b200_adam: no usable CUDA device";
+    case B200_ADAM_E_NO_DEVICE: return "b200_adam: the current CUDA device is not a compute-capability-10.x (B200) device";
     default: break;
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
