@@ -76,7 +76,7 @@ CUDA_SOURCE = "src/adam_op/adam_op_impl_cuda.cu"
 
 def build_cuda(force: bool = False, verbose: bool = True) -> str | None:
     """Optional comparison point "O4": the reference's UNMODIFIED CUDA adam_op (src/adam_op/adam_op_impl_cuda.cu,
-    -D__USE_CUDA__) compiled as is for sm_100 -> oracle/_ref/cuda/_C.so.  Used only by tools/leaf_sweep.py to time
+    -D__USE_CUDA__) compiled as is for sm_100 -> oracle/_ref/cuda/_C.so.  Used only by tests/perf/leaf_sweep.py to time
     "the reference's generic kernels recompiled for B200" beside this repo's kernels.  ~4 minutes of nvcc."""
     srcs = SOURCES + [CUDA_SOURCE]
     if not all(os.path.isfile(os.path.join(REF, s)) for s in srcs):

@@ -3,14 +3,14 @@
 multi-tensor launches, this repo's kernels vs the reference's own CUDA adam_op recompiled for sm_100
 (oracle/_ref/cuda/_C.so, built from the unmodified sources by `python oracle/build_ref.py --cuda`).
 
-    python tools/leaf_sweep.py --out gpurun_out/leaf_sweep.json         # on the GPU box
+    python tests/perf/leaf_sweep.py --out gpurun_out/leaf_sweep.json    # on the GPU box
 
 "ours"      : fused forward + fused backward through the C ABI (2 launches per step, any number of leaves)
 "reference" : what autograd runs per leaf per step with the reference extension: forward_mu, forward_nu,
               forward_updates, backward_updates, 2 accumulation adds, backward_mu, backward_nu, 1 add
               (accelerated_op/adam_op.py:168-180,105-121,53-60,79-86) -- 9 launches per leaf per step.
 Timing: CUDA events, 5 warm-ups + 20 iterations; sizes whose working set fits the 126 MB L2 are marked.
-This is TEST/BENCH infrastructure (it loads oracle/_ref); nothing in the product imports it.
+This is TEST infrastructure (it lives under tests/ because it loads oracle/_ref/cuda); nothing in the product imports it.
 """
 from __future__ import annotations
 
@@ -20,7 +20,7 @@ import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 B1, B2, EPS, ER, CNT = 0.9, 0.999, 1e-8, 1e-8, 3
