@@ -79,6 +79,11 @@ def test_step_counters_host_mirror_cpu():
     bare = [torch.tensor(41), torch.tensor(7)]       # user-built counters without a mirror
     new = inc_count_flat([torch.ones(1), torch.ones(1)], bare)
     assert [int(c) for c in new] == [42, 8] and count_as_int(3) == 3
+    # an in-place edit of a tagged counter bumps its version: the stale mirror must not be used
+    new[0].fill_(100)
+    assert count_as_int(new[0]) == 100 and new[0]._b200_host_count == 100
+    again = inc_count_flat([torch.ones(1), torch.ones(1)], new)
+    assert [int(c) for c in again] == [101, 9]
 
 
 def test_transform_validation_and_none_leaves_cpu():

@@ -26,14 +26,28 @@ from torchopt_b200._native import adam_op
 INT64_MAX = torch.iinfo(torch.int64).max
 
 
+def tag_count(count: torch.Tensor, host: int) -> torch.Tensor:
+    """Attach the host mirror of a step counter to its device tensor, together with the tensor's version so that an
+    in-place edit of the counter (which bumps the version) invalidates the mirror."""
+    count._b200_host_count = host  # type: ignore[attr-defined]
+    count._b200_host_version = count._version  # type: ignore[attr-defined]
+    return count
+
+
 def count_as_int(count: Any) -> int:
-    """Step count as a Python int.  A tensor tagged by ``torchopt_b200.transform`` answers from its host mirror;
-    an untagged tensor is read with ``int()`` (a device->host sync -- what the reference's pybind ``size_t``
-    conversion does on every call, accelerated_op/adam_op.py:98-101)."""
+    """Step count as a Python int.  A tensor tagged by ``torchopt_b200.transform`` answers from its host mirror as long
+    as it has not been modified in place since; otherwise (untagged or edited tensor) it is read with ``int()`` -- a
+    device->host sync, which is what the reference's pybind ``size_t`` conversion does on EVERY call
+    (accelerated_op/adam_op.py:98-101) -- and re-tagged."""
     if isinstance(count, int):
         return count
     host = getattr(count, "_b200_host_count", None)
-    return int(count) if host is None else host
+    if host is not None and getattr(count, "_b200_host_version", None) == count._version:
+        return host
+    host = int(count)
+    if isinstance(count, torch.Tensor):
+        tag_count(count, host)
+    return host
 
 
 class AdamOp:  # pylint: disable=too-few-public-methods

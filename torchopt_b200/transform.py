@@ -19,7 +19,7 @@ from typing import Any, Callable, NamedTuple, Sequence
 import torch
 
 from torchopt_b200 import _pytree
-from torchopt_b200.accelerated_op.adam_op import INT64_MAX, AdamOp, count_as_int
+from torchopt_b200.accelerated_op.adam_op import INT64_MAX, AdamOp, count_as_int, tag_count
 
 
 # A/B switch for parity tests: False routes the differentiable path through the reference's three-node graph
@@ -46,9 +46,7 @@ class ScaleByAdamState(NamedTuple):
 STATE_DTYPE = {torch.bfloat16: torch.float32}
 
 
-def _tag(count: torch.Tensor, host: int) -> torch.Tensor:
-    count._b200_host_count = host  # type: ignore[attr-defined]
-    return count
+_tag = tag_count
 
 
 def make_counts(values: Sequence[int | None], devices: Sequence[torch.device | None]) -> list:
@@ -115,9 +113,7 @@ def inc_count_flat(updates: Sequence, counts: Sequence) -> list:
         if g is None or c is None:
             values.append(None), devices.append(None)
             continue
-        host = count_as_int(c)
-        if getattr(c, "_b200_host_count", None) is None and isinstance(c, torch.Tensor):
-            _tag(c, host)
+        host = count_as_int(c)   # tags an untagged / edited counter after reading it once
         values.append(host + (host != INT64_MAX))
         devices.append(c.device if isinstance(c, torch.Tensor) else torch.device("cpu"))
     fresh = make_counts(values, devices)
