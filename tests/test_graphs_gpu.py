@@ -1,0 +1,105 @@
+"""CUDA-graph capture of whole unrolls (torchopt_b200.graphs): a replay must reproduce the eager computation --
+bit-for-bit where only element-wise kernels are involved -- on fresh inputs, with no host launches of the Adam kernels."""
+from __future__ import annotations
+
+import pytest
+import torch
+
+gpu = pytest.mark.gpu
+
+
+def test_capture_needs_cuda_when_absent():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import torchopt_b200 as tb
+    with pytest.raises(RuntimeError, match="CUDA"):
+        tb.graphs.capture(lambda: None)
+
+
+@gpu
+@pytest.mark.parametrize("mrg", [False, True])
+def test_captured_unroll_equals_eager_bitwise(mrg):
+    """5-step FuncAdam unroll + meta-backward over ragged leaves: replay on NEW inputs == eager on the same inputs."""
+    import torchopt_b200 as tb
+    dev = torch.device("cuda")
+    torch.manual_seed(11)
+    sizes = [5, 64, 320, 4097, 36_864, 100_003]
+    params = [(torch.randn(k, device=dev) * 0.1).requires_grad_(True) for k in sizes]
+
+    def meta_grad(*ws):
+        opt = tb.FuncAdam(1e-2, eps_root=1e-8, moment_requires_grad=mrg)
+        cur = list(params)
+        for _ in range(5):
+            cur = opt.apply_gradients([w * p for w, p in zip(ws, cur)], cur)
+        outer = torch.stack([(p * p).sum() for p in cur]).sum()
+        return torch.autograd.grad(outer, params)
+
+    ws0 = [torch.rand(k, device=dev) + 0.5 for k in sizes]
+    step = tb.graphs.capture(meta_grad, *ws0)
+    for trial in range(3):
+        ws = [torch.rand(k, device=dev) + 0.25 * (trial + 1) for k in sizes]
+        want = meta_grad(*ws)
+        before = tb.abi.kernel_launches()
+        got = step(*ws)
+        torch.cuda.synchronize()
+        assert tb.abi.kernel_launches() == before, "a replay must not go through the host launch path"
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+    # parameters edited in place are picked up too (they are read by the recorded kernels, not copied)
+    with torch.no_grad():
+        for p in params:
+            p.mul_(1.5)
+    want = meta_grad(*ws0)
+    got = step(*ws0)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+
+
+@gpu
+def test_captured_maml_task_accumulates_into_bucket():
+    """MetaAdam inner loop on a module + query loss + backward() into a GradBucket, captured once and replayed per task:
+    same meta-gradient as the eager loop (matmul-based net; tolerance covers cuBLAS algorithm choice only)."""
+    import torch.nn.functional as F
+    from torch import nn
+
+    import torchopt_b200 as tb
+    from torchopt_b200.parallel import GradBucket
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = nn.Sequential(nn.Linear(20, 33), nn.Tanh(), nn.Linear(33, 5)).to(dev)
+    slots = [(m, k) for m in net.modules() for k, p in m._parameters.items() if p is not None]
+    meta = [m._parameters[k] for m, k in slots]
+    bucket = GradBucket(meta)
+    tasks = 4
+    xs, ys = torch.randn(tasks, 16, 20, device=dev), torch.randint(0, 5, (tasks, 16), device=dev)
+    xq, yq = torch.randn(tasks, 24, 20, device=dev), torch.randint(0, 5, (tasks, 24), device=dev)
+
+    def rebind():
+        for (m, k), p in zip(slots, meta):
+            m._parameters[k] = p
+
+    def task_backward(x_s, y_s, x_q, y_q):
+        rebind()
+        inner = tb.MetaAdam(net, lr=1e-2, moment_requires_grad=True)
+        for _ in range(3):
+            inner.step(F.cross_entropy(net(x_s), y_s))
+        loss = F.cross_entropy(net(x_q), y_q) / tasks
+        rebind()
+        loss.backward()
+        return loss.detach()
+
+    bucket.zero()
+    eager_losses = [task_backward(xs[t], ys[t], xq[t], yq[t]).clone() for t in range(tasks)]
+    want = [p.grad.clone() for p in meta]
+
+    step = tb.graphs.capture(task_backward, xs[0], ys[0], xq[0], yq[0], before_each=bucket.zero)
+    for _ in range(2):  # two meta-iterations: zero between them, replays accumulate
+        bucket.zero()
+        losses = [step(xs[t], ys[t], xq[t], yq[t]).clone() for t in range(tasks)]
+        torch.cuda.synchronize()
+        for a, b in zip(losses, eager_losses):
+            torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
+        for p, w in zip(meta, want):
+            torch.testing.assert_close(p.grad, w, rtol=1e-5, atol=1e-7)
+    assert step.replays == 2 * tasks
