@@ -251,40 +251,60 @@ def resnet18_unroll(tb, torch, iters: int = 10) -> dict:
         outer = torch.stack([p.sum() for p in cur]).sum()
         return torch.autograd.grad(outer, params)
 
-    def timed():
+    def timed(fn):
         for _ in range(3):
-            once()
+            fn()
         torch.cuda.synchronize()
         l0 = tb.abi.kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(iters):
-            once()
+            fn()
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters, (tb.abi.kernel_launches() - l0) // iters
 
     n = sum(RESNET18_LEAVES)
-    ms, launches = timed()
+    ms, launches = timed(once)
     optim.FUSE_STEP = False
     try:
-        ms_chain, launches_chain = timed()
+        ms_chain, launches_chain = timed(once)
     finally:
         optim.FUSE_STEP = True
-    # the same unroll recorded once in a CUDA graph (torchopt_b200.graphs) and replayed: no eager dispatch at all
+
+    def graphed(fn, reps):
+        """(ms per replay, outputs) of fn captured once in a CUDA graph (torchopt_b200.graphs) and replayed."""
+        step = tb.graphs.capture(fn)
+        for _ in range(3):
+            got = step()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps, got
+
     want = [g.clone() for g in once()]
-    step = tb.graphs.capture(once)
-    for _ in range(3):
-        got = step()
-    torch.cuda.synchronize()
+    ms_graph, got = graphed(once, iters * 5)
     same = all(torch.equal(a, b) for a, b in zip(got, want))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters * 5):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms_graph = e0.elapsed_time(e1) / (iters * 5)
+
+    # flat-buffer layout (torchopt_b200.flat, SURVEY.md 8f n4): the 62 leaves packed into ONE buffer, so the inner loss
+    # gradient is one multiply and every optimizer step one single-range launch; the meta-gradient still arrives per
+    # original leaf (views of the flat gradient through the pack's backward)
+    lay = tb.FlatLayout(params)
+    w_flat = lay.pack(ws)
+
+    def once_flat():
+        opt = tb.FuncAdam(1e-3, eps_root=EPS_ROOT, moment_requires_grad=False)
+        cur = lay.pack(params)
+        for _ in range(5):
+            (cur,) = opt.apply_gradients([w_flat * cur], [cur])
+        return torch.autograd.grad(cur.sum(), params)
+
+    ms_flat, launches_flat = timed(once_flat)
+    same_flat = all(torch.equal(a, b) for a, b in zip(once_flat(), want))
+    ms_flat_graph, _ = graphed(once_flat, iters * 5)
     return {"workload": "ResNet-18-sized pytree (62 leaves, 11689512 fp32 params), 5-step unroll + meta-backward, "
                         "public API (FuncAdam) incl. autograd + one torch multiply per leaf per step",
             "ms_per_unroll": ms, "gelem_per_s": n * 5 / (ms * 1e-3) / 1e9,
@@ -293,6 +313,14 @@ def resnet18_unroll(tb, torch, iters: int = 10) -> dict:
                            "bit_identical_to_eager": same,
                            "note": "whole unroll + meta-backward captured once (torchopt_b200.graphs.capture), "
                                    "one cudaGraphLaunch per unroll"},
+            "flat_layout": {"ms_per_unroll": ms_flat, "gelem_per_s": n * 5 / (ms_flat * 1e-3) / 1e9,
+                            "adam_kernel_launches_per_unroll": launches_flat,
+                            "cuda_graph_ms_per_unroll": ms_flat_graph,
+                            "cuda_graph_gelem_per_s": n * 5 / (ms_flat_graph * 1e-3) / 1e9,
+                            "bit_identical_to_per_leaf": same_flat,
+                            "note": "leaves packed into one 128-B-aligned buffer (torchopt_b200.FlatLayout): one "
+                                    "multiply + one single-range launch per step each way; includes the pack and "
+                                    "the per-leaf meta-gradient views"},
             "chained_path": {"ms_per_unroll": ms_chain, "adam_kernel_launches_per_unroll": launches_chain,
                              "note": "scale_by_accelerated_adam launch + torch mul(-lr) + torch add per leaf"}}
 

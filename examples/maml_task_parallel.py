@@ -42,12 +42,13 @@ def make_net(n_way: int) -> nn.Module:
 class TaskRunner:
     """Runs the inner loop of one task on a module whose parameter slots are re-bound to the meta-parameters."""
 
-    def __init__(self, net: nn.Module, inner_steps: int, lr: float):
-        self.net, self.inner_steps, self.lr = net, inner_steps, lr
+    def __init__(self, net: nn.Module, inner_steps: int, lr: float, streams: int = 1):
+        self.net, self.inner_steps, self.lr, self.streams = net, inner_steps, lr, max(1, streams)
         self.slots = [(m, k) for m in net.modules() for k, p in m._parameters.items() if p is not None]
         self.meta_params = [m._parameters[k] for m, k in self.slots]
         self.bucket = GradBucket(self.meta_params)   # every .grad is a view of ONE flat buffer
-        self.task_graph = None
+        self.task_graphs: list = []
+        self.buckets: list = []
 
     def rebind(self):
         for (m, k), p in zip(self.slots, self.meta_params):
@@ -72,16 +73,25 @@ class TaskRunner:
     def meta_grads_graphed(self, data, tasks, num_tasks) -> list:
         """Same as ``meta_grads`` with one task's whole computation (5 inner MetaAdam steps, query loss, meta-backward
         accumulating into the bucket) recorded ONCE in a CUDA graph and replayed per task: 4 small input copies +
-        one graph launch per task instead of ~2 500 eager kernel launches and their autograd bookkeeping."""
+        one graph launch per task instead of ~2 500 eager kernel launches and their autograd bookkeeping.  With
+        ``streams`` > 1 that many independently captured instances replay side by side (tasks are independent; one
+        task alone keeps only a few SMs busy), each into its own flat gradient buffer; the buffers are then summed."""
         x_spt, y_spt, x_qry, y_qry = data
-        if self.task_graph is None:
+        if not self.task_graphs:
             def one_task(xs, ys, xq, yq):
                 (self.query_loss(xs, ys, xq, yq) / num_tasks).backward()
-            self.task_graph = tb.graphs.capture(one_task, x_spt[0], y_spt[0], x_qry[0], y_qry[0],
-                                                before_each=self.bucket.zero)
-        self.bucket.zero()
-        for t in tasks:
-            self.task_graph(x_spt[t], y_spt[t], x_qry[t], y_qry[t])
+            # instance j accumulates into its own flat gradient buffer (the .grad views attached while it is recorded)
+            self.buckets = [self.bucket] + [GradBucket(self.meta_params) for _ in range(self.streams - 1)]
+            for b in self.buckets:
+                self.task_graphs.append(tb.graphs.capture(one_task, x_spt[0], y_spt[0], x_qry[0], y_qry[0],
+                                                          before_each=b.zero))
+        for b in self.buckets:
+            b.zero()
+        self.bucket.attach()
+        tb.graphs.replay_concurrently(self.task_graphs, ((x_spt[t], y_spt[t], x_qry[t], y_qry[t]) for t in tasks))
+        for b in self.buckets[1:]:           # fixed summation order: deterministic result
+            for flat, other in zip(self.bucket.buffers.values(), b.buffers.values()):
+                flat.add_(other)
         return [p.grad for p in self.meta_params]
 
 
@@ -92,6 +102,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay one captured CUDA graph per task (torchopt_b200.graphs)")
+    ap.add_argument("--streams", type=int, default=1, help="with --graph: captured instances replayed concurrently")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -112,7 +123,7 @@ def main():
     T = args.tasks
     data = (torch.randn(T, 25, 1, 28, 28, device=dev, generator=gen), torch.randint(0, 5, (T, 25), device=dev, generator=gen),
             torch.randn(T, 75, 1, 28, 28, device=dev, generator=gen), torch.randint(0, 5, (T, 75), device=dev, generator=gen))
-    runner = TaskRunner(net, args.inner_steps, lr=1e-3)
+    runner = TaskRunner(net, args.inner_steps, lr=1e-3, streams=args.streams)
     meta_opt = torch.optim.Adam(runner.meta_params, lr=1e-3)
     mine = task_slice(T, rank, world)
     n_params = sum(p.numel() for p in runner.meta_params)
@@ -156,7 +167,7 @@ def main():
     if rank == 0:
         best = min(times[1:] or times)
         print(json.dumps({"workload": "MAML 5-way 5-shot, 32-task meta-batch, 5 inner MetaAdam steps, 75205-param CNN",
-                          "n_gpus": world, "tasks_per_rank": len(mine), "params": n_params, "cuda_graph": args.graph,
+                          "n_gpus": world, "tasks_per_rank": len(mine), "params": n_params, "cuda_graph": args.graph, "streams": args.streams if args.graph else 1,
                           "ms_per_meta_iter": best, "tasks_per_s": T / (best * 1e-3),
                           "adam_kernel_launches_per_rank_per_iter": launches,
                           "max_rel_diff_vs_single_process": max_rel if args.check else None}))

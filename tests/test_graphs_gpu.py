@@ -103,3 +103,16 @@ def test_captured_maml_task_accumulates_into_bucket():
         for p, w in zip(meta, want):
             torch.testing.assert_close(p.grad, w, rtol=1e-5, atol=1e-7)
     assert step.replays == 2 * tasks
+
+
+    # two more instances with their own gradient buffers, replayed side by side on their own streams
+    buckets = [GradBucket(meta) for _ in range(2)]
+    inst = [tb.graphs.capture(task_backward, xs[0], ys[0], xq[0], yq[0], before_each=b.zero) for b in buckets]
+    for b in buckets:
+        b.zero()
+    issued = tb.graphs.replay_concurrently(inst, ((xs[t], ys[t], xq[t], yq[t]) for t in range(tasks)))
+    assert issued == tasks and [i.replays for i in inst] == [2, 2]
+    total = [a + b for a, b in zip(buckets[0].views, buckets[1].views)]
+    torch.cuda.synchronize()
+    for got, w in zip(total, want):
+        torch.testing.assert_close(got, w, rtol=1e-5, atol=1e-7)
