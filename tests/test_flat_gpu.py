@@ -84,7 +84,7 @@ def test_flat_meta_adam_equals_per_leaf(variant):
     # meta-gradients: the same addends, but a parameter used several times by the loss has >2 gradient contributions and
     # the autograd engine sums them in a different order (per view first, then with the step's dp) -> last-bit noise
     for a, b in zip(g_flat, g_leaf):
-        torch.testing.assert_close(a, b, rtol=2e-6, atol=1e-9)
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=1e-7)
 
 
 @gpu
