@@ -364,6 +364,33 @@ def whole_step_kernels(abi, torch, n: int = 1 << 28, iters: int = 20) -> dict:
     return res
 
 
+def link_ceiling(torch, dev, mib: int = 512) -> dict:
+    """What the host<->device link gives plain pinned copies running in BOTH directions at once (two streams):
+    the ceiling of the e2e leg, which moves 24 B/elem each way (tools/pcie_ceiling.py is the stand-alone version)."""
+    n = mib << 20
+    h_in, h_out = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in, d_out = torch.empty(n, dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = float("inf")
+    for _ in range(4):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream()
+        e0.record()
+        s1.wait_stream(cur), s2.wait_stream(cur)
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+        cur.wait_stream(s1), cur.wait_stream(s2)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    each = n / 1e9 / (best * 1e-3)
+    return {"bidir_each_GBps": each, "ceiling_gelem_per_s": each / 24.0,
+            "how": f"{mib} MiB pinned H2D + {mib} MiB D2H concurrently on two streams, best of 4"}
+
+
 # ---------------------------------------------------------------------------------------------------------
 def run_b200(args) -> None:
     import torch
@@ -470,6 +497,9 @@ def run_b200(args) -> None:
                          f"size-independent), API torchopt_b200.adam_op.host_step -> b200_adam_host_step_f32"}
         tb._C.host_release()
         del hin, hout
+        if rank == 0 and world == 1:
+            e2e["link"] = link_ceiling(torch, dev)
+            e2e["link"]["frac"] = e2e["value"] / e2e["link"]["ceiling_gelem_per_s"]
 
     extra = None
     if rank == 0 and world == 1 and not args.no_extra:
