@@ -171,3 +171,38 @@ def test_maml_inner_loop_meta_gradients(inner_steps, eps_root, mrg):
             continue
         assert torch.isfinite(a).all()
         assert torch.equal(a, b) and torch.equal(a, c), f"meta-gradient of {name} differs between dispatch paths"
+
+
+@pytest.mark.parametrize("recipe", ["adam", "adamw"])
+def test_functional_api_over_a_dict_pytree(recipe):
+    """The reference drives ``torchopt.adam`` with the dict returned by ``named_parameters`` (tests/test_alias.py:231-247:
+    ``params = dict(model.named_parameters())``, ``optim.update(grads, state, params=params)``,
+    ``torchopt.apply_updates``).  Dict / nested pytrees must give exactly what the flat leaf list gives."""
+    import torchopt_b200 as tb
+    model, _, loader = make(torch.float32, zero_inputs=False)
+    make_opt = tb.adam if recipe == "adam" else tb.adamw
+    names = [k for k, _ in model.named_parameters()]
+
+    def run(as_tree):
+        opt = make_opt(1e-2, weight_decay=1e-2, eps_root=1e-8)
+        leaves = [p.detach().clone().requires_grad_(True) for _, p in model.named_parameters()]
+        params = dict(zip(names, leaves)) if as_tree else leaves
+        buffers = {k: v.clone() for k, v in model.named_buffers()}
+        state = opt.init(params)
+        for x, y in loader:
+            named = params if as_tree else dict(zip(names, params))
+            loss = nn.functional.cross_entropy(functional_call(model, {**named, **buffers}, (x,)), y)
+            flat = list(named.values())
+            grads = torch.autograd.grad(loss, flat, allow_unused=True)
+            grads = dict(zip(named.keys(), grads)) if as_tree else list(grads)
+            updates, state = opt.update(grads, state, params=params, inplace=False)
+            new = tb.apply_updates(params, updates, inplace=False)
+            if as_tree:
+                assert isinstance(updates, dict) and isinstance(new, dict) and list(new) == sorted(names)
+                params = {k: v.detach().requires_grad_(True) for k, v in new.items()}
+            else:
+                params = [v.detach().requires_grad_(True) for v in new]
+        return [params[k] for k in names] if as_tree else params
+
+    for a, b in zip(run(True), run(False)):
+        assert torch.equal(a, b)

@@ -14,6 +14,7 @@ from typing import Any, Iterable, Sequence
 import torch
 from torch import nn
 
+from torchopt_b200 import _pytree
 from torchopt_b200.accelerated_op.adam_step import AdamStep
 from torchopt_b200.transform import (GradientTransformation, ScaleByAdamState, inc_count_flat,
                                      scale_by_accelerated_adam)
@@ -36,6 +37,23 @@ def chain_flat(*transforms: GradientTransformation) -> GradientTransformation:
             updates, s = t.update(updates, s, params=params, inplace=inplace)
             new_state.append(s)
         return updates, tuple(new_state)
+
+    return GradientTransformation(init_fn, update_fn)
+
+
+def with_flattened_tree(inner: GradientTransformation) -> GradientTransformation:
+    """Let a transformation written for flat leaf lists accept arbitrary pytrees (dicts, nested lists / tuples,
+    namedtuples; ``None`` is a leaf) -- base.py:203-237 / combine.py:49-102: ``init`` and ``update`` flatten their
+    arguments, the state stays flat, the updates come back in the structure they arrived in."""
+
+    def init_fn(params: Any) -> Any:
+        return inner.init(_pytree.tree_flatten(params)[0])
+
+    def update_fn(updates: Any, state: Any, *, params: Any = None, inplace: bool = True):
+        leaves, spec = _pytree.tree_flatten(updates)
+        flat_params = None if params is None else _pytree.tree_flatten(params)[0]
+        new_leaves, state = inner.update(leaves, state, params=flat_params, inplace=inplace)
+        return _pytree.tree_unflatten(spec, new_leaves), state
 
     return GradientTransformation(init_fn, update_fn)
 
@@ -88,18 +106,19 @@ def flip_sign_and_add_weight_decay(weight_decay: float = 0.0, maximize: bool = F
 def adam(lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, *,
          eps_root: float = 0.0, moment_requires_grad: bool = False, maximize: bool = False,
          use_accelerated_op: bool = True) -> GradientTransformation:
-    """Functional Adam over flat leaf lists with the accelerated op (alias/adam.py:55-137)."""
+    """Functional Adam with the accelerated op (alias/adam.py:55-137).  ``init`` / ``update`` take any pytree of
+    tensors (a flat list is the common case); the state keeps flat leaf lists."""
     if not use_accelerated_op:
         raise NotImplementedError("torchopt_b200 only provides the accelerated-op path (use_accelerated_op=True)")
     if not (callable(lr) or lr >= 0.0):
         raise ValueError(f"Invalid learning rate: {lr}")
     b1, b2 = betas
-    return chain_flat(
+    return with_flattened_tree(chain_flat(
         flip_sign_and_add_weight_decay(weight_decay, maximize),
         scale_by_accelerated_adam.flat(b1=b1, b2=b2, eps=eps, eps_root=eps_root,
                                        moment_requires_grad=moment_requires_grad),
         scale(-lr),
-    )
+    ))
 
 
 def add_decayed_weights(weight_decay: float = 0.0):
@@ -129,7 +148,7 @@ def add_decayed_weights(weight_decay: float = 0.0):
 def adamw(lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2, *,
           eps_root: float = 0.0, mask: Any = None, moment_requires_grad: bool = False, maximize: bool = False,
           use_accelerated_op: bool = True) -> GradientTransformation:
-    """Functional AdamW over flat leaf lists with the accelerated op (alias/adamw.py:57-151)."""
+    """Functional AdamW with the accelerated op (alias/adamw.py:57-151); pytrees as in ``adam``."""
     if not use_accelerated_op:
         raise NotImplementedError("torchopt_b200 only provides the accelerated-op path (use_accelerated_op=True)")
     if mask is not None:
@@ -137,19 +156,25 @@ def adamw(lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999), eps: floa
     if not (callable(lr) or lr >= 0.0):
         raise ValueError(f"Invalid learning rate: {lr}")
     b1, b2 = betas
-    return chain_flat(
+    return with_flattened_tree(chain_flat(
         flip_sign_and_add_weight_decay(0.0, maximize),
         scale_by_accelerated_adam.flat(b1=b1, b2=b2, eps=eps, eps_root=eps_root,
                                        moment_requires_grad=moment_requires_grad),
         add_decayed_weights(weight_decay),
         scale(-lr),
-    )
+    ))
 
 
-def apply_updates(params: Sequence, updates: Sequence, *, inplace: bool = True) -> list:
-    """``p + u`` per leaf (update.py:39-81): in place on ``p.data`` or as a new differentiable tensor."""
+def apply_updates(params: Any, updates: Any, *, inplace: bool = True) -> Any:
+    """``p + u`` per leaf (update.py:39-81): in place on ``p.data`` or as a new differentiable tensor.  ``params`` and
+    ``updates`` are pytrees of the same structure (flat lists included); the result has the structure of ``params``
+    (a flat sequence comes back as a list)."""
+    leaves, spec = _pytree.tree_flatten(params)
+    ups = _pytree.tree_flatten(updates)[0]
+    if len(ups) != len(leaves):
+        raise ValueError("apply_updates: params and updates have different structures")
     out = []
-    for p, u in zip(params, updates):
+    for p, u in zip(leaves, ups):
         if u is None:
             out.append(p)
         elif inplace:
@@ -157,7 +182,9 @@ def apply_updates(params: Sequence, updates: Sequence, *, inplace: bool = True) 
             out.append(p)
         else:
             out.append(p.add(u))
-    return out
+    if spec.kind in ("list", "tuple") and all(c.kind == "leaf" for c in spec.children):
+        return out
+    return _pytree.tree_unflatten(spec, out)
 
 
 def _fused_chain_step(step_op: AdamStep, params: list, grads: list, state: tuple) -> tuple[list, tuple]:
