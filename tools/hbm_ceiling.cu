@@ -1,7 +1,7 @@
 // hbm_ceiling.cu -- what does B200 HBM deliver to a TRIVIAL stream kernel with the same read:write mix as the
 // Adam kernels?  ("speed of light" evidence.)
 //
-//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I torchopt_b200/csrc tools/hbm_ceiling.cu -o build/hbm_ceiling
+//   python -c "import __graft_entry__ as g; g.build()"    (-> build/hbm_ceiling)
 //   build/hbm_ceiling [log2_n=28] [iters=20]
 //
 // Each kernel reads R fp32 arrays and writes W fp32 arrays of n elements with the engine's access pattern

@@ -82,8 +82,31 @@ def build_shim(force: bool = False, verbose: bool = True) -> str:
     return SHIM
 
 
+def build_tools(force: bool = False, verbose: bool = True) -> list[str]:
+    """Stand-alone measurement programs under tools/*.cu (HBM ceiling, TMA staging experiment) -> build/<name>.
+    Not part of the product; built here so that every CUDA source in the tree is compiled for sm_100a by one entry."""
+    tools = os.path.join(ROOT, "tools")
+    out_dir = os.path.join(ROOT, "build")
+    os.makedirs(out_dir, exist_ok=True)
+    built = []
+    for name in sorted(f for f in os.listdir(tools) if f.endswith(".cu")):
+        src, exe = os.path.join(tools, name), os.path.join(out_dir, name[:-3])
+        if force or not _newer(exe, [src, os.path.join(CSRC, "adam_kernels.cuh")]):
+            # linked against the product library (some tools time their variant against the product kernel)
+            cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+                   "--fmad=false", f"-I{INCLUDE}", f"-I{CSRC}", src, f"-L{PKG}", "-lb200adam",
+                   "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../torchopt_b200", "-o", exe]
+            if verbose:
+                print("[torchopt_b200] " + " ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+        built.append(exe)
+    return built
+
+
 def build(force: bool = False, verbose: bool = True) -> tuple[str, str]:
-    return build_lib(force, verbose), build_shim(force, verbose)
+    out = build_lib(force, verbose), build_shim(force, verbose)
+    build_tools(force, verbose)
+    return out
 
 
 if __name__ == "__main__":
