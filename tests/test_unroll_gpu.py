@@ -3,7 +3,6 @@
 reference's own AdamOp + compiled adam_op on CPU (tests/golden/make_golden.py)."""
 from __future__ import annotations
 
-import numpy as np
 import pytest
 
 from conftest import assert_bits_equal

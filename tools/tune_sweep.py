@@ -12,7 +12,6 @@ torchopt_b200/csrc/b200_adam.cu.
 from __future__ import annotations
 
 import argparse
-import itertools
 import json
 import os
 import subprocess
