@@ -152,6 +152,20 @@ class FlatMetaAdam:
         self.flat_p = new_flat
         self._bind(new_flat)
 
+    def stop_gradient_(self) -> None:
+        """Cut the unroll here (torchopt.stop_gradient semantics): the flat parameters and the moments become graph
+        leaves that keep ``requires_grad``, and the module's slots are re-bound to views of the detached buffer."""
+        self.flat_p = self.flat_p.detach().requires_grad_(True)
+        if self.state is not None:
+            def cut(t: Any) -> Any:
+                if isinstance(t, torch.Tensor) and t.grad_fn is not None:
+                    return t.detach().requires_grad_(True)
+                return t
+            self.state = tuple(
+                ScaleByAdamState(mu=[cut(t) for t in st.mu], nu=[cut(t) for t in st.nu], count=st.count)
+                if isinstance(st, ScaleByAdamState) else st for st in self.state)
+        self._bind(self.flat_p)
+
     # per-task state save / restore is a reference swap (utils.py:309-349 walks the tree and clones)
     def state_dict(self) -> Any:
         return (self.flat_p, self.state)
