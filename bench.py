@@ -325,6 +325,102 @@ def resnet18_unroll(tb, torch, iters: int = 10) -> dict:
                              "note": "scale_by_accelerated_adam launch + torch mul(-lr) + torch add per leaf"}}
 
 
+def config0_mlp1m(tb, torch, iters: int = 10) -> dict:
+    """BASELINE configs[0], the reference's own CPU-runnable case: 784-1024-256-10 MLP (1 068 810 params, 6 leaves),
+    batch 64, 5 inner differentiable Adam steps + meta-gradient w.r.t. the initial parameters.  Timed three ways:
+    this repo on the GPU (eager MetaAdam; the same unroll captured in one CUDA graph) and the reference's path on the
+    host cores (oracle/ref_unroll.RefMetaAdam: its compiled OpenMP adam_op driven per leaf by its three autograd
+    Functions -- test infrastructure, pinned to golden vectors by tests/test_oracle.py)."""
+    import torch.nn.functional as F
+    from torch import nn
+
+    def make(dev, dtype=torch.float32):
+        torch.manual_seed(1)
+        net = nn.Sequential(nn.Linear(784, 1024), nn.ReLU(), nn.Linear(1024, 256), nn.ReLU(), nn.Linear(256, 10))
+        return net.to(device=dev, dtype=dtype)
+
+    gen = torch.Generator().manual_seed(0)
+    x_cpu, y_cpu = torch.randn(64, 784, generator=gen), torch.randint(0, 10, (64,), generator=gen)
+
+    def unroll(net, inner_cls, x, y):
+        slots = [(m, k) for m in net.modules() for k, p in m._parameters.items() if p is not None]
+        init = [m._parameters[k] for m, k in slots]
+        inner = inner_cls(net, lr=1e-3, moment_requires_grad=True)
+        for _ in range(5):
+            inner.step(F.cross_entropy(net(x), y))
+        meta = torch.autograd.grad(F.cross_entropy(net(x), y), init)
+        for (m, k), p in zip(slots, init):
+            m._parameters[k] = p
+        return meta
+
+    dev = torch.device("cuda")
+    net_gpu, x, y = make(dev), x_cpu.to(dev), y_cpu.to(dev)
+    n_params = sum(p.numel() for p in net_gpu.parameters())
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    def gpu_once():
+        return unroll(net_gpu, tb.MetaAdam, x, y)
+
+    for _ in range(3):
+        meta_gpu = gpu_once()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        gpu_once()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_eager = e0.elapsed_time(e1) / iters
+    step = tb.graphs.capture(gpu_once)
+    for _ in range(3):
+        meta_graph = step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters * 5):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_graph = e0.elapsed_time(e1) / (iters * 5)
+    graph_same = all(torch.equal(a, b) for a, b in zip(meta_graph, meta_gpu))
+    out = {"workload": f"784-1024-256-10 MLP ({n_params} fp32 params, 6 leaves), batch 64, 5 inner MetaAdam steps + "
+                       f"meta-gradient w.r.t. the initial parameters (BASELINE configs[0])",
+           "b200_eager_ms": ms_eager, "b200_cuda_graph_ms": ms_graph, "cuda_graph_bit_identical_to_eager": graph_same}
+
+    from oracle import adam_oracle as ao   # CPU-baseline leg
+    if ao.load_ref() is None:
+        out["reference_cpu"] = {"unavailable": "oracle/_ref/_C.so not built"}
+        return out
+    from oracle.ref_unroll import RefMetaAdam
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    net_cpu = make("cpu")
+
+    def cpu_once():
+        return unroll(net_cpu, RefMetaAdam, x_cpu, y_cpu)
+
+    meta_cpu = cpu_once()
+    best = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter()
+        cpu_once()
+        best = min(best, time.perf_counter() - t0)
+    def rel(a_list, b_list):
+        return max(float((a.cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30)) for a, b in zip(a_list, b_list))
+
+    worst = rel(meta_gpu, meta_cpu)
+    # the same unroll in fp64 on both sides: the GPU's and the CPU's matrix multiplies round differently and Adam's
+    # normalisation amplifies that in fp32; in fp64 the two pipelines must agree to ~1e-9 if they compute the same thing
+    net64_gpu, net64_cpu = make(dev, torch.float64), make("cpu", torch.float64)
+    worst64 = rel(unroll(net64_gpu, tb.MetaAdam, x.double(), y), unroll(net64_cpu, RefMetaAdam, x_cpu.double(), y_cpu))
+    out["reference_cpu"] = {"ms": best * 1e3, "cores": cores, "kind": "reference kernels (oracle/_ref) + restated "
+                            "Python glue (oracle/ref_unroll.py)", "sample": "the whole unroll, best of 3 after 1 warm-up",
+                            "max_rel_diff_of_meta_gradient_gpu_vs_cpu_fp32": worst,
+                            "max_rel_diff_of_meta_gradient_gpu_vs_cpu_fp64": worst64}
+    out["speedup_eager_vs_reference_cpu"] = best * 1e3 / ms_eager
+    out["speedup_cuda_graph_vs_reference_cpu"] = best * 1e3 / ms_graph
+    return out
+
+
 def whole_step_kernels(abi, torch, n: int = 1 << 28, iters: int = 20) -> dict:
     """Whole-optimizer-step kernels (Adam + scale(-lr) + apply_updates in one launch each way) through
     the C ABI on one flat n-element fp32 leaf: forward 28 B/elem (p, g, mu, nu -> p', mu', nu'), backward 36 B/elem
@@ -508,7 +604,8 @@ def run_b200(args) -> None:
         torch.cuda.empty_cache()
         extra = {}
         for key, fn in (("resnet18_unroll5", lambda: resnet18_unroll(tb, torch)),
-                        ("whole_step_kernels", lambda: whole_step_kernels(abi, torch))):
+                        ("whole_step_kernels", lambda: whole_step_kernels(abi, torch)),
+                        ("config0_mlp1m", lambda: config0_mlp1m(tb, torch))):
             try:
                 extra[key] = fn()
             except Exception as exc:  # noqa: BLE001  the headline number must survive a failure of a side measurement

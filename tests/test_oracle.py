@@ -130,3 +130,42 @@ def test_host_scalars_match_c(c_oracle):
             assert s["O1"] == lib.oracle_adam_one_minus_pow(ctypes.c_double(b1), ctypes.c_uint64(cnt))
             assert s["C2E"] == lib.oracle_adam_inv_one_minus_pow_eps(
                 ctypes.c_double(b2), ctypes.c_double(1e-8), ctypes.c_uint64(cnt))
+
+
+@pytest.mark.parametrize("tag,dt", [("f32", np.float32), ("f64", np.float64)])
+def test_ref_unroll_reproduces_golden(golden, tag, dt):
+    """oracle/ref_unroll.py (the restated Python glue of the reference's AdamOp over its compiled CPU kernels) reproduces
+    the golden 5-step unroll -- values AND meta-gradients -- that tests/golden/make_golden.py recorded with the
+    reference's own accelerated_op/adam_op.py.  This pins the harness bench.py uses for BASELINE config [0]."""
+    import torch
+    from oracle import adam_oracle as ao
+    from oracle.ref_unroll import make_ref_adam_op
+    ref = ao.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/_C.so not built")
+    torch.set_num_threads(1)
+    z = golden(f"adam_unroll_{tag}.npz")
+    AdamOp = make_ref_adam_op(ref.adam_op)
+    lr = float(z["lr"])
+    for mrg in (False, True):
+        for er in (0.0, 1e-8):
+            op = AdamOp(b1=0.9, b2=0.999, eps=1e-8, eps_root=er, inplace=False)
+            p = torch.from_numpy(z["p0"].copy()).requires_grad_(True)
+            wt = torch.from_numpy(z["w"].copy()).requires_grad_(True)
+            mu = torch.from_numpy(z["mu0"].copy()).requires_grad_(mrg)
+            nu = torch.from_numpy(z["nu0"].copy()).requires_grad_(mrg)
+            t = torch.from_numpy(z["tgt"].copy())
+            cur, cmu, cnu = p, mu, nu
+            for k in range(z["w"].shape[0]):
+                cmu, cnu, u = op(cmu, cnu, wt[k] * cur, k + 1)
+                cur = cur + (-lr) * u
+            outer = ((cur - t) ** 2).sum() + (cmu * t).sum() + (cnu * t * t).sum()
+            grads = torch.autograd.grad(outer, [p, wt] + ([mu, nu] if mrg else []))
+            key = f"mrg{int(mrg)}.er{er:g}."
+            assert_bits_equal(cur.detach().numpy(), z[key + "p_final"], key + "p_final")
+            assert_bits_equal(cmu.detach().numpy(), z[key + "mu_final"], key + "mu_final")
+            assert_bits_equal(grads[0].numpy(), z[key + "d_p0"], key + "d_p0")
+            assert_bits_equal(grads[1].numpy(), z[key + "d_w"], key + "d_w")
+            if mrg:
+                assert_bits_equal(grads[2].numpy(), z[key + "d_mu0"], key + "d_mu0")
+                assert_bits_equal(grads[3].numpy(), z[key + "d_nu0"], key + "d_nu0")

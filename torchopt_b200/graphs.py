@@ -58,19 +58,29 @@ class CapturedCallable:
         # the allocator's steady state must all exist before the recording starts.
         side = self.stream = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
-                if before_each is not None:
-                    before_each()
-                out = fn(*self.static_inputs)
-                del out
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        if before_each is not None:
-            before_each()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, pool=pool, stream=self.stream):
-            self.outputs = fn(*self.static_inputs)
+        # Leaf parameters created on the default stream keep their gradient-accumulator node there; autograd warns
+        # about that on every backward run from another stream.  The stream hand-over is explicit here (wait_stream
+        # before, synchronize after, capture on the same private stream), so the warning is noise for this block.
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    if before_each is not None:
+                        before_each()
+                    out = fn(*self.static_inputs)
+                    del out
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            if before_each is not None:
+                before_each()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, pool=pool, stream=self.stream):
+                self.outputs = fn(*self.static_inputs)
+        finally:
+            if quiet is not None:
+                quiet(True)
         self.replays = 0
 
     def pool(self) -> Any:
