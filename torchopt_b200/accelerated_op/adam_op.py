@@ -25,6 +25,11 @@ from torchopt_b200._native import adam_op
 
 INT64_MAX = torch.iinfo(torch.int64).max
 
+# A/B switch for parity tests: True runs the fused differentiable path through the NATIVE autograd node
+# (torch_shim.cpp:FusedNode -- the same kernels and saved tensors without ~200 us of interpreter bookkeeping per
+# 62-leaf call); False through the Python autograd.Function below (AdamOp.FusedOp), kept as the readable specification.
+NATIVE_NODE = True
+
 
 def tag_count(count: torch.Tensor, host: int) -> torch.Tensor:
     """Attach the host mirror of a step counter to its device tensor, together with the tensor's version so that an
@@ -162,9 +167,15 @@ class AdamOp:  # pylint: disable=too-few-public-methods
             new_nu = self.NuOp.apply(updates, nu, self.b2)
             new_updates = self.UpdatesOp.apply(new_mu, new_nu, (self.b1, self.b2, self.eps, self.eps_root, count))
             return new_mu, new_nu, new_updates
-        new_mu, new_nu, new_updates = self.FusedOp.apply(
-            (self.b1, self.b2, self.eps, self.eps_root), (count,), updates, mu, nu)
+        new_mu, new_nu, new_updates = self._fused((count,), (updates,), (mu,), (nu,))
         return new_mu, new_nu, new_updates
+
+    def _fused(self, counts: Sequence[int], updates: Sequence, mus: Sequence, nus: Sequence) -> Sequence:
+        """``mu'_0.., nu'_0.., u_0..`` through one autograd node (native or Python, see NATIVE_NODE)."""
+        if NATIVE_NODE:
+            return adam_op.fused_autograd(list(updates), list(mus), list(nus), self.b1, self.b2, self.eps,
+                                          self.eps_root, list(counts))
+        return self.FusedOp.apply((self.b1, self.b2, self.eps, self.eps_root), tuple(counts), *updates, *mus, *nus)
 
     def multi(self, mus: Sequence[torch.Tensor | None], nus: Sequence[torch.Tensor | None],
               updates: Sequence[torch.Tensor | None], counts: Sequence[Any],
@@ -188,9 +199,8 @@ class AdamOp:  # pylint: disable=too-few-public-methods
             triples = [self(mus[i], nus[i], updates[i], c) for i, c in zip(live, host_counts)]
             out_mu, out_nu, out_u = zip(*triples)
         else:
-            flat = self.FusedOp.apply(
-                (self.b1, self.b2, self.eps, self.eps_root), host_counts,
-                *[updates[i] for i in live], *[mus[i] for i in live], *[nus[i] for i in live])
+            flat = self._fused(host_counts, [updates[i] for i in live], [mus[i] for i in live],
+                               [nus[i] for i in live])
             k = len(live)
             out_mu, out_nu, out_u = flat[:k], flat[k:2 * k], flat[2 * k:]
         for j, i in enumerate(live):

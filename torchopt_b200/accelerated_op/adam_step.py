@@ -22,6 +22,10 @@ import torch
 from torchopt_b200._native import adam_op
 from torchopt_b200.accelerated_op.adam_op import count_as_int
 
+# A/B switch for parity tests: True = native autograd node (torch_shim.cpp:StepNode), False = the Python
+# autograd.Function below (AdamStep.Op), kept as the readable specification of the node.
+NATIVE_NODE = True
+
 
 class AdamStep:  # pylint: disable=too-few-public-methods
     """``AdamStep(...)(params, grads, mu, nu, counts) -> (new_params, new_mu, new_nu)`` for a whole recipe:
@@ -89,8 +93,14 @@ class AdamStep:  # pylint: disable=too-few-public-methods
                                wd_l2, wd_dec, maximize)
             return new_p, new_mu, new_nu
         k = len(live)
-        flat = self.Op.apply(self.hyper, host_counts, *[params[i] for i in live], *[grads[i] for i in live],
-                             *[mus[i] for i in live], *[nus[i] for i in live])
+        if NATIVE_NODE:
+            b1, b2, eps, eps_root, step_size, wd_l2, wd_dec, maximize = self.hyper
+            flat = adam_op.step_autograd([params[i] for i in live], [grads[i] for i in live], [mus[i] for i in live],
+                                         [nus[i] for i in live], b1, b2, eps, eps_root, step_size, list(host_counts),
+                                         wd_l2, wd_dec, maximize)
+        else:
+            flat = self.Op.apply(self.hyper, host_counts, *[params[i] for i in live], *[grads[i] for i in live],
+                                 *[mus[i] for i in live], *[nus[i] for i in live])
         for j, i in enumerate(live):
             new_p[i], new_mu[i], new_nu[i] = flat[j], flat[k + j], flat[2 * k + j]
         return new_p, new_mu, new_nu

@@ -14,6 +14,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 #include <torch/extension.h>
+#include <torch/csrc/autograd/custom_function.h>
 #include <ATen/ExpandUtils.h>
 
 #include <array>
@@ -496,6 +497,166 @@ fused_step_backward(
   return {dg, dmu, dnu, dp};
 }
 
+// ---- native autograd nodes ----------------------------------------------------------------------------
+// The Python autograd.Function wrappers (accelerated_op/adam_op.py:FusedOp, adam_step.py:AdamStep.Op) spend ~200 us per
+// call on a 62-leaf pytree in THPFunction bookkeeping (248 inputs / 186 outputs), 3x the launch itself.  These C++
+// nodes do the same thing -- same kernels, same saved tensors, same None handling -- without the interpreter, and their
+// backward runs on the autograd engine's thread without taking the GIL.
+using torch::autograd::AutogradContext;
+using torch::autograd::variable_list;
+
+inline std::vector<size_t> to_counts(const std::vector<int64_t> &c) { return std::vector<size_t>(c.begin(), c.end()); }
+inline OptTensor opt(const Tensor &t) { return t.defined() ? OptTensor(t) : OptTensor(); }
+inline Tensor undef(const OptTensor &t) { return t.has_value() ? *t : Tensor(); }
+
+// tensors = g_0.., mu_0.., nu_0.. ; hyper = b1, b2, eps, eps_root ; outputs mu'_0.., nu'_0.., u_0..
+struct FusedNode : public torch::autograd::Function<FusedNode> {
+  static variable_list forward(AutogradContext *ctx, at::TensorList tensors, std::vector<int64_t> counts,
+                               std::vector<double> hyper) {
+    const size_t L = counts.size();
+    std::vector<OptTensor> g(L);
+    std::vector<Tensor> mu(L), nu(L);
+    for (size_t i = 0; i < L; ++i) g[i] = tensors[i], mu[i] = tensors[L + i], nu[i] = tensors[2 * L + i];
+    auto out = fused_forward(g, mu, nu, hyper[0], hyper[1], hyper[2], hyper[3], to_counts(counts), false);
+    auto &new_mu = std::get<0>(out);
+    auto &new_nu = std::get<1>(out);
+    auto &new_u = std::get<2>(out);
+    ctx->set_materialize_grads(false);  // absent gradients stay undefined -> the kernel skips those streams
+    ctx->saved_data["counts"] = counts;
+    ctx->saved_data["hyper"] = hyper;
+    variable_list saved, result;
+    saved.reserve(3 * L), result.reserve(3 * L);
+    for (size_t i = 0; i < L; ++i) saved.push_back(tensors[i]);   // g
+    for (size_t i = 0; i < L; ++i) saved.push_back(*new_u[i]);    // u
+    for (size_t i = 0; i < L; ++i) saved.push_back(new_mu[i]);    // mu'
+    ctx->save_for_backward(saved);
+    for (size_t i = 0; i < L; ++i) result.push_back(new_mu[i]);
+    for (size_t i = 0; i < L; ++i) result.push_back(new_nu[i]);
+    for (size_t i = 0; i < L; ++i) result.push_back(*new_u[i]);
+    return result;
+  }
+
+  static variable_list backward(AutogradContext *ctx, variable_list douts) {
+    const auto counts = ctx->saved_data["counts"].toIntVector();
+    const auto hyper = ctx->saved_data["hyper"].toDoubleVector();
+    const size_t L = counts.size();
+    const variable_list saved = ctx->get_saved_variables();
+    std::vector<Tensor> g(saved.begin(), saved.begin() + L), u(saved.begin() + L, saved.begin() + 2 * L),
+        new_mu(saved.begin() + 2 * L, saved.end());
+    std::vector<OptTensor> dme(L), dne(L), du(L);
+    std::vector<bool> need_g(L), need_mu(L), need_nu(L);
+    for (size_t i = 0; i < L; ++i) {
+      dme[i] = opt(douts[i]), dne[i] = opt(douts[L + i]), du[i] = opt(douts[2 * L + i]);
+      need_g[i] = ctx->needs_input_grad(i), need_mu[i] = ctx->needs_input_grad(L + i);
+      need_nu[i] = ctx->needs_input_grad(2 * L + i);
+    }
+    auto out = fused_backward(du, dme, dne, u, new_mu, g, need_g, need_mu, need_nu, hyper[0], hyper[1], hyper[3],
+                              to_counts(counts));
+    variable_list grads;
+    grads.reserve(3 * L + 2);
+    for (size_t i = 0; i < L; ++i) grads.push_back(undef(std::get<0>(out)[i]));
+    for (size_t i = 0; i < L; ++i) grads.push_back(undef(std::get<1>(out)[i]));
+    for (size_t i = 0; i < L; ++i) grads.push_back(undef(std::get<2>(out)[i]));
+    grads.emplace_back(), grads.emplace_back();  // counts, hyper
+    return grads;
+  }
+};
+
+// tensors = p_0.., g_0.., mu_0.., nu_0.. ; hyper = b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize ;
+// outputs p'_0.., mu'_0.., nu'_0..
+struct StepNode : public torch::autograd::Function<StepNode> {
+  static variable_list forward(AutogradContext *ctx, at::TensorList tensors, std::vector<int64_t> counts,
+                               std::vector<double> hyper) {
+    const size_t L = counts.size();
+    std::vector<Tensor> p(L), mu(L), nu(L);
+    std::vector<OptTensor> g(L);
+    for (size_t i = 0; i < L; ++i)
+      p[i] = tensors[i], g[i] = tensors[L + i], mu[i] = tensors[2 * L + i], nu[i] = tensors[3 * L + i];
+    auto out = fused_step(p, g, mu, nu, hyper[0], hyper[1], hyper[2], hyper[3], hyper[4], to_counts(counts), false, false,
+                          hyper[5], hyper[6], hyper[7] != 0.0);
+    auto &new_p = std::get<0>(out);
+    auto &new_mu = std::get<1>(out);
+    auto &new_nu = std::get<2>(out);
+    ctx->set_materialize_grads(false);
+    ctx->saved_data["counts"] = counts;
+    ctx->saved_data["hyper"] = hyper;
+    // u is recomputed in the backward kernel; the raw parameters are needed only to re-derive g + wd*p
+    variable_list saved, result;
+    for (size_t i = 0; i < L; ++i) saved.push_back(tensors[L + i]);
+    for (size_t i = 0; i < L; ++i) saved.push_back(new_mu[i]);
+    for (size_t i = 0; i < L; ++i) saved.push_back(new_nu[i]);
+    if (hyper[5] != 0.0)
+      for (size_t i = 0; i < L; ++i) saved.push_back(tensors[i]);
+    ctx->save_for_backward(saved);
+    result.reserve(3 * L);
+    for (size_t i = 0; i < L; ++i) result.push_back(new_p[i]);
+    for (size_t i = 0; i < L; ++i) result.push_back(new_mu[i]);
+    for (size_t i = 0; i < L; ++i) result.push_back(new_nu[i]);
+    return result;
+  }
+
+  static variable_list backward(AutogradContext *ctx, variable_list douts) {
+    const auto counts = ctx->saved_data["counts"].toIntVector();
+    const auto hyper = ctx->saved_data["hyper"].toDoubleVector();
+    const size_t L = counts.size();
+    const bool l2 = hyper[5] != 0.0;
+    const variable_list saved = ctx->get_saved_variables();
+    std::vector<Tensor> g(saved.begin(), saved.begin() + L), new_mu(saved.begin() + L, saved.begin() + 2 * L),
+        new_nu(saved.begin() + 2 * L, saved.begin() + 3 * L);
+    std::vector<OptTensor> params(L), dp_in(L), dus(L), dme(L), dne(L);
+    std::vector<bool> need_p(L), need_g(L), need_mu(L), need_nu(L);
+    for (size_t i = 0; i < L; ++i) {
+      if (l2) params[i] = saved[3 * L + i];
+      dp_in[i] = opt(douts[i]), dme[i] = opt(douts[L + i]), dne[i] = opt(douts[2 * L + i]);
+      need_p[i] = ctx->needs_input_grad(i), need_g[i] = ctx->needs_input_grad(L + i);
+      need_mu[i] = ctx->needs_input_grad(2 * L + i), need_nu[i] = ctx->needs_input_grad(3 * L + i);
+    }
+    auto out = fused_step_backward(dp_in, dus, dme, dne, new_mu, new_nu, g, need_g, need_mu, need_nu, hyper[0], hyper[1],
+                                   hyper[2], hyper[3], hyper[4], to_counts(counts), params, need_p, hyper[5], hyper[6],
+                                   hyper[7] != 0.0);
+    variable_list grads;
+    grads.reserve(4 * L + 2);
+    for (size_t i = 0; i < L; ++i) grads.push_back(undef(std::get<3>(out)[i]));  // dparams
+    for (size_t i = 0; i < L; ++i) grads.push_back(undef(std::get<0>(out)[i]));  // dgrads
+    for (size_t i = 0; i < L; ++i) grads.push_back(undef(std::get<1>(out)[i]));  // dmu
+    for (size_t i = 0; i < L; ++i) grads.push_back(undef(std::get<2>(out)[i]));  // dnu
+    grads.emplace_back(), grads.emplace_back();  // counts, hyper
+    return grads;
+  }
+};
+
+// Python entry points: all lists hold one tensor per leaf (no None: the callers filter leaves without a gradient)
+std::vector<Tensor> fused_autograd(const std::vector<Tensor> &updates, const std::vector<Tensor> &mu,
+                                   const std::vector<Tensor> &nu, double b1, double b2, double eps, double eps_root,
+                                   const std::vector<int64_t> &count) {
+  const size_t L = updates.size();
+  if (mu.size() != L || nu.size() != L || count.size() != L)
+    throw std::runtime_error("fused_autograd: updates, mu, nu and count must have the same number of leaves");
+  std::vector<Tensor> flat;
+  flat.reserve(3 * L);
+  flat.insert(flat.end(), updates.begin(), updates.end());
+  flat.insert(flat.end(), mu.begin(), mu.end());
+  flat.insert(flat.end(), nu.begin(), nu.end());
+  return FusedNode::apply(at::TensorList(flat), count, std::vector<double>{b1, b2, eps, eps_root});
+}
+
+std::vector<Tensor> step_autograd(const std::vector<Tensor> &params, const std::vector<Tensor> &grads,
+                                  const std::vector<Tensor> &mu, const std::vector<Tensor> &nu, double b1, double b2,
+                                  double eps, double eps_root, double step_size, const std::vector<int64_t> &count,
+                                  double wd_l2, double wd_decoupled, bool maximize) {
+  const size_t L = params.size();
+  if (grads.size() != L || mu.size() != L || nu.size() != L || count.size() != L)
+    throw std::runtime_error("step_autograd: params, grads, mu, nu and count must have the same number of leaves");
+  std::vector<Tensor> flat;
+  flat.reserve(4 * L);
+  flat.insert(flat.end(), params.begin(), params.end());
+  flat.insert(flat.end(), grads.begin(), grads.end());
+  flat.insert(flat.end(), mu.begin(), mu.end());
+  flat.insert(flat.end(), nu.begin(), nu.end());
+  return StepNode::apply(at::TensorList(flat), count,
+                         std::vector<double>{b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize ? 1.0 : 0.0});
+}
+
 // host-buffer step (CPU tensors in, CPU tensors out, work done on the current CUDA device)
 std::array<Tensor, 6> host_step(const Tensor &g, const Tensor &mu, const Tensor &nu, const Tensor &du,
                                 const Tensor &dmu_ext, const Tensor &dnu_ext, std::array<Tensor, 6> out, double b1,
@@ -557,6 +718,15 @@ PYBIND11_MODULE(_C, mod) {
         py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("step_size"), py::arg("count"),
         py::arg("params"), py::arg("need_dparams"), py::arg("wd_l2") = 0.0, py::arg("wd_decoupled") = 0.0,
         py::arg("maximize") = false);
+  m.def("fused_autograd", &fused_autograd,
+        "fused_forward as ONE native autograd node (backward = fused_backward): returns mu'.., nu'.., u..",
+        py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("b1"), py::arg("b2"), py::arg("eps"),
+        py::arg("eps_root"), py::arg("count"));
+  m.def("step_autograd", &step_autograd,
+        "fused_step as ONE native autograd node (backward = fused_step_backward): returns p'.., mu'.., nu'..",
+        py::arg("params"), py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("b1"), py::arg("b2"),
+        py::arg("eps"), py::arg("eps_root"), py::arg("step_size"), py::arg("count"), py::arg("wd_l2") = 0.0,
+        py::arg("wd_decoupled") = 0.0, py::arg("maximize") = false);
   m.def("host_step", &host_step, "Fused forward+backward over pinned HOST tensors (pipelined H2D/compute/D2H)",
         py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("dupdates"), py::arg("dmu_ext"), py::arg("dnu_ext"),
         py::arg("out"), py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("count"),
