@@ -126,6 +126,24 @@ def ncu_traffic() -> dict | None:
         return None
 
 
+def mix_ceiling(reads: int, writes: int):
+    """Best GB/s a TRIVIAL add-only kernel with the same read:write mix reached on B200 (tools/hbm_ceiling.cu, committed
+    measurement profiles/r01_hbm_ceiling.jsonl) -- the memory system's ceiling for this access mix."""
+    best = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_hbm_ceiling.jsonl")) as f:
+            for line in f:
+                try:
+                    rec = json.loads(line)
+                except ValueError:
+                    continue
+                if rec.get("reads") == reads and rec.get("writes") == writes and "kind" not in rec:
+                    best = max(best or 0.0, float(rec["GBps"]))
+    except OSError:
+        return None
+    return best
+
+
 def _scaled_traffic(traffic: dict | None, which: str, n: int):
     """Measured DRAM bytes per launch for an n-element launch: ncu's per-element figure x n (the capture is taken at
     a smaller n so that ncu's kernel replay stays cheap; bytes/elem is size-independent for these streams)."""
@@ -562,6 +580,8 @@ def run_b200(args) -> None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     elapsed_ms = float(tmax.item())
     clocks = sampler.summary(wall0, wall1) if sampler else None
+    if sampler:
+        sampler.stop()
 
     # ---- e2e: public host-buffer API, pinned host arrays in and out, copies inside the timed region ----
     e2e = None
@@ -655,7 +675,11 @@ def run_b200(args) -> None:
                      "forward": {"achieved": ach_fwd, "frac": ach_fwd / peak, "avg_launch_ms": fwd_avg_ms,
                                  "algorithmic_bytes_per_launch": BYTES_FWD * n,
                                  "traffic": _scaled_traffic(traffic, "forward", n)},
-                     "step_hbm_gbs_per_gpu": step_gbs, "step_frac": step_gbs / peak},
+                     "step_hbm_gbs_per_gpu": step_gbs, "step_frac": step_gbs / peak,
+                     "trivial_kernel_same_mix": {
+                         "backward_6r3w_GBps": mix_ceiling(6, 3), "forward_3r3w_GBps": mix_ceiling(3, 3),
+                         "pure_read_GBps": mix_ceiling(1, 0),
+                         "source": "profiles/r01_hbm_ceiling.jsonl (tools/hbm_ceiling.cu, add-only kernels, n=2^28)"}},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "cpu_baseline": cpu_baseline,
     }
     if extra:

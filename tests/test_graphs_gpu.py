@@ -116,3 +116,50 @@ def test_captured_maml_task_accumulates_into_bucket():
     torch.cuda.synchronize()
     for got, w in zip(total, want):
         torch.testing.assert_close(got, w, rtol=1e-5, atol=1e-7)
+
+
+@gpu
+@pytest.mark.parametrize("path", ["whole_step", "chained_dict"])
+def test_capture_after_eager_runs_and_no_garbage(path):
+    """Eager runs on the default stream followed by a capture of the same function: nothing of the eager graphs may
+    survive (a leaf's gradient-accumulator node created on the default stream would make the capture illegal), and a
+    step must not leave reference cycles behind."""
+    import gc
+    import weakref
+
+    import torchopt_b200 as tb
+    dev = torch.device("cuda")
+    torch.manual_seed(2)
+    sizes = [9408, 64, 64, 36_864]
+    params = [(torch.randn(k, device=dev) * 0.1).requires_grad_(True) for k in sizes]
+    lay = tb.FlatLayout(params)
+    w_flat = lay.pack([torch.rand(k, device=dev) + 0.5 for k in sizes])
+    probe = []
+
+    def fn():
+        cur = lay.pack(params)
+        if path == "whole_step":
+            opt = tb.FuncAdam(1e-3, eps_root=1e-8)
+            (cur,) = opt.apply_gradients([w_flat * cur], [cur])
+        else:
+            opt = tb.adam(1e-3, eps_root=1e-8)
+            tree = {"w": cur}
+            state = opt.init(tree)
+            updates, state = opt.update({"w": w_flat * cur}, state, params=tree, inplace=False)
+            cur = tb.apply_updates(tree, updates, inplace=False)["w"]
+        probe[:] = [weakref.ref(cur)]
+        return torch.autograd.grad(cur.sum(), params)
+
+    gc.collect()
+    gc.disable()
+    try:
+        want = [g.clone() for g in fn()]
+        assert probe[0]() is None, "the unrolled tensors of an eager run outlived it (reference cycle)"
+        kept = fn()                                   # results of an eager run kept alive across the capture
+        step = tb.graphs.capture(fn)
+    finally:
+        gc.enable()
+    got = step()
+    torch.cuda.synchronize()
+    for a, b, c in zip(got, want, kept):
+        assert torch.equal(a, b) and torch.equal(a, c)

@@ -226,3 +226,29 @@ def test_grad_bucket_single_process():
         p.grad = None
     bucket.zero()
     assert w[0].grad is bucket.views[0] and float(flat.abs().sum()) == 0.0
+
+
+def test_pytree_helpers_leave_no_reference_cycles():
+    """tree_flatten / tree_unflatten / tree_map must not create garbage: a self-referential closure would keep the leaves
+    -- tensors with their autograd graphs -- alive until the next gc pass (memory held across unrolled steps, and stale
+    gradient-accumulator nodes that break CUDA-graph capture after an eager run)."""
+    import gc
+    import weakref
+
+    import torch
+    from torchopt_b200 import _pytree
+    gc.collect()
+    gc.disable()
+    try:
+        a = torch.randn(5, requires_grad=True)
+        t = a * 2
+        ref = weakref.ref(t)
+        tree = {"x": [t, None], "y": (t + 1,)}
+        leaves, spec = _pytree.tree_flatten(tree)
+        back = _pytree.tree_unflatten(spec, leaves)
+        mapped = _pytree.tree_map(lambda v: v, tree)
+        del t, tree, leaves, back, mapped
+        assert ref() is None, "a pytree helper kept the leaves alive (reference cycle)"
+    finally:
+        gc.enable()
+    assert gc.collect() == 0

@@ -17,6 +17,7 @@ raise ``RuntimeError('Not implemented')`` from the native module.
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Sequence
 
 import torch
@@ -28,7 +29,7 @@ INT64_MAX = torch.iinfo(torch.int64).max
 # A/B switch for parity tests: True runs the fused differentiable path through the NATIVE autograd node
 # (torch_shim.cpp:FusedNode -- the same kernels and saved tensors without ~200 us of interpreter bookkeeping per
 # 62-leaf call); False through the Python autograd.Function below (AdamOp.FusedOp), kept as the readable specification.
-NATIVE_NODE = True
+NATIVE_NODE = os.environ.get("B200_ADAM_PY_NODES", "") in ("", "0")
 
 
 def tag_count(count: torch.Tensor, host: int) -> torch.Tensor:

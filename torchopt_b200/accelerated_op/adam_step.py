@@ -15,6 +15,7 @@ are folded into the same launch (``x.add(y, alpha=a)`` evaluated as ATen does on
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Sequence
 
 import torch
@@ -24,7 +25,7 @@ from torchopt_b200.accelerated_op.adam_op import count_as_int
 
 # A/B switch for parity tests: True = native autograd node (torch_shim.cpp:StepNode), False = the Python
 # autograd.Function below (AdamStep.Op), kept as the readable specification of the node.
-NATIVE_NODE = True
+NATIVE_NODE = os.environ.get("B200_ADAM_PY_NODES", "") in ("", "0")
 
 
 class AdamStep:  # pylint: disable=too-few-public-methods

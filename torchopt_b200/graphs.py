@@ -26,6 +26,7 @@ capture only; a replay re-executes the recorded GPU work on the static inputs an
 """
 from __future__ import annotations
 
+import gc
 from typing import Any, Callable
 
 import torch
@@ -56,6 +57,10 @@ class CapturedCallable:
         # that may be replaying at the same time.
         # Warm-up first: cuDNN / cuBLAS handles, workspaces and autotuning, lazy module loading of every kernel, and
         # the allocator's steady state must all exist before the recording starts.
+        # Autograd graphs of earlier eager runs that are only kept alive by unreachable Python cycles would also keep the
+        # leaves' gradient-accumulator nodes alive -- bound to the stream they were created on (normally the default
+        # stream); the recorded backward would then have to synchronise with that stream, which a capture forbids.
+        gc.collect()
         side = self.stream = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         # Leaf parameters created on the default stream keep their gradient-accumulator node there; autograd warns
