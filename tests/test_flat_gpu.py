@@ -37,9 +37,9 @@ def test_layout_offsets_pack_and_views_cpu():
 class Elementwise(nn.Module):
     """A 'network' made of element-wise maps only, so that the two layouts must agree bit for bit."""
 
-    def __init__(self, sizes, dev):
+    def __init__(self, sizes, dev, dtype=torch.float32):
         super().__init__()
-        self.ps = nn.ParameterList([nn.Parameter(torch.randn(k, device=dev) * 0.3) for k in sizes])
+        self.ps = nn.ParameterList([nn.Parameter((torch.randn(k, device=dev) * 0.3).to(dtype)) for k in sizes])
 
     def forward(self, ws):
         return torch.stack([(w * p * p).sum() for w, p in zip(ws, self.ps)]).sum()
@@ -49,13 +49,14 @@ SIZES = [5, 64, 321, 4097, 36_864]
 
 
 @gpu
-@pytest.mark.parametrize("variant", ["adam", "adam_l2", "adamw"])
-def test_flat_meta_adam_equals_per_leaf(variant):
+@pytest.mark.parametrize("variant,dtype", [("adam", torch.float32), ("adam_l2", torch.float32), ("adamw", torch.float32),
+                                           ("adam", torch.float64), ("adamw", torch.bfloat16)])
+def test_flat_meta_adam_equals_per_leaf(variant, dtype):
     import torchopt_b200 as tb
     dev = torch.device("cuda")
     torch.manual_seed(5)
-    net = Elementwise(SIZES, dev)
-    ws = [[torch.rand(k, device=dev) + 0.5 for k in SIZES] for _ in range(4)]
+    net = Elementwise(SIZES, dev, dtype)
+    ws = [[(torch.rand(k, device=dev) + 0.5).to(dtype) for k in SIZES] for _ in range(4)]
     kw = {"adam": {}, "adam_l2": {"weight_decay": 0.05}, "adamw": {"weight_decay": 0.05}}[variant]
     per_leaf = tb.MetaAdamW if variant == "adamw" else tb.MetaAdam
     flat_cls = tb.FlatMetaAdamW if variant == "adamw" else tb.FlatMetaAdam
@@ -83,8 +84,9 @@ def test_flat_meta_adam_equals_per_leaf(variant):
         assert torch.equal(a, b), "unrolled parameters are bit-identical in both layouts"
     # meta-gradients: the same addends, but a parameter used several times by the loss has >2 gradient contributions and
     # the autograd engine sums them in a different order (per view first, then with the step's dp) -> last-bit noise
+    rtol, atol = {torch.float32: (2e-5, 1e-7), torch.float64: (1e-12, 1e-15), torch.bfloat16: (5e-2, 1e-2)}[dtype]
     for a, b in zip(g_flat, g_leaf):
-        torch.testing.assert_close(a, b, rtol=2e-5, atol=1e-7)
+        torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
 
 
 @gpu
