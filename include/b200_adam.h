@@ -154,6 +154,15 @@ int b200_adam_step_inplace(int dtype, int64_t num_leaves, void *const *p, void *
                            double eps_root, double step_size, double wd_l2, double wd_decoupled, int maximize,
                            void *stream);
 
+/* Same, with a choice about the gradient arrays: overwrite_grads != 0 is b200_adam_step_inplace (the reference's side
+ * effect: with inplace=True its chain turns every gradient tensor into the scaled update, transform/scale.py:98-101,
+ * update.py:76-77); overwrite_grads == 0 leaves g untouched -- p, mu, nu are still updated in place -- which saves the
+ * 4 B/element store: 28 instead of 32 B/element fp32.  For optimizers that own their gradient buffer (FlatAdam). */
+int b200_adam_step_inplace_ex(int dtype, int64_t num_leaves, void *const *p, void *const *g, void *const *mu,
+                              void *const *nu, const int64_t *n, const uint64_t *count, double b1, double b2,
+                              double eps, double eps_root, double step_size, double wd_l2, double wd_decoupled,
+                              int maximize, int overwrite_grads, void *stream);
+
 /* Backward of b200_adam_step_forward.  Incoming per leaf (each may be NULL): dp = gradient of p_out, dus = gradient of
  * us_out (the array argument itself may be NULL), dmu_ext / dnu_ext = gradients of mu_out / nu_out.
  *   du2 = (dp + dus) * step_size ; then exactly b200_adam_fused_backward with u recomputed from new_mu, new_nu and the

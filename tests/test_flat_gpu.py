@@ -153,8 +153,10 @@ def test_flat_adam_inplace_equals_per_leaf_bitwise(decoupled):
             first = next(iter(net_b.parameters()))
             first.grad = first.grad.clone()
         l0 = tb.abi.kernel_launches()
+        g_before = opt_b.flat_g.clone()
         opt_b.step()
         assert tb.abi.kernel_launches() - l0 == 1
+        assert torch.equal(opt_b.flat_g, g_before), "FlatAdam leaves its gradient buffer untouched (28 B/elem step)"
         opt_a.step()
         for p, q in zip(net_a.parameters(), net_b.parameters()):
             assert torch.equal(p, q)

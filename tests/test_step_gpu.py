@@ -70,6 +70,13 @@ def test_step_kernels_vs_oracle_composition(c_oracle, tag):
                              er, -lr, s)
             for got, want, name in ((a, w_p, "p"), (b, w_us, "g<-us"), (c, w_mu, "mu"), (d, w_nu, "nu")):
                 assert_bits_equal(host(got), want, f"step_inplace {name} n={n}")
+            # in place, gradients left untouched (b200_adam_step_inplace_ex, overwrite_grads = 0) and overwritten (= 1)
+            for overwrite in (False, True):
+                a, b, c, d = P.clone(), G.clone(), MU.clone(), NU.clone()
+                abi.step_inplace(dt, [a.data_ptr()], [b.data_ptr()], [c.data_ptr()], [d.data_ptr()], [n], [cnt], B1, B2,
+                                 EPS, er, -lr, s, overwrite_grads=overwrite)
+                for got, want, name in ((a, w_p, "p"), (b, w_us if overwrite else g, "g"), (c, w_mu, "mu"), (d, w_nu, "nu")):
+                    assert_bits_equal(host(got), want, f"step_inplace_ex(overwrite={overwrite}) {name} n={n}")
             # backward: FULL, LAST and GENERIC presence patterns (incl. a gradient on the scaled update)
             M2, V2 = dev(w_mu), dev(w_nu)
             for hdp, hdus, hme, hne in ((1, 0, 1, 1), (1, 0, 0, 0), (1, 1, 1, 0), (0, 1, 0, 1), (0, 0, 1, 1), (1, 0, 0, 1)):

@@ -43,6 +43,8 @@ SYMBOLS = {
                                        c_void_p]),
     "b200_adam_step_inplace": (c_int, [c_int, c_int64, _vpp, _vpp, _vpp, _vpp, _i64p, _u64p, c_double, c_double,
                                        c_double, c_double, c_double, c_double, c_double, c_int, c_void_p]),
+    "b200_adam_step_inplace_ex": (c_int, [c_int, c_int64, _vpp, _vpp, _vpp, _vpp, _i64p, _u64p, c_double, c_double,
+                                          c_double, c_double, c_double, c_double, c_double, c_int, c_int, c_void_p]),
     "b200_adam_step_backward": (c_int, [c_int, c_int64, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp,
                                         _vpp, _vpp, _i64p, _u64p, c_double, c_double, c_double, c_double, c_double,
                                         c_double, c_double, c_int, c_void_p]),
@@ -157,11 +159,19 @@ def step_forward(dtype, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, count, b
 
 
 def step_inplace(dtype, p, g, mu, nu, n, count, b1, b2, eps, eps_root, step_size, stream=0, wd_l2=0.0,
-                 wd_decoupled=0.0, maximize=False):
+                 wd_decoupled=0.0, maximize=False, overwrite_grads=None):
+    """``overwrite_grads=None`` calls b200_adam_step_inplace (g <- scaled update, the reference's side effect);
+    True / False call b200_adam_step_inplace_ex with that choice."""
     L = len(n)
-    check(load().b200_adam_step_inplace(dtype, L, _ptrs(p), _ptrs(g), _ptrs(mu), _ptrs(nu), _arr(c_int64, n),
-                                        _arr(c_uint64, count), b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled,
-                                        int(maximize), stream), "step_inplace")
+    if overwrite_grads is None:
+        check(load().b200_adam_step_inplace(dtype, L, _ptrs(p), _ptrs(g), _ptrs(mu), _ptrs(nu), _arr(c_int64, n),
+                                            _arr(c_uint64, count), b1, b2, eps, eps_root, step_size, wd_l2,
+                                            wd_decoupled, int(maximize), stream), "step_inplace")
+    else:
+        check(load().b200_adam_step_inplace_ex(dtype, L, _ptrs(p), _ptrs(g), _ptrs(mu), _ptrs(nu), _arr(c_int64, n),
+                                               _arr(c_uint64, count), b1, b2, eps, eps_root, step_size, wd_l2,
+                                               wd_decoupled, int(maximize), int(bool(overwrite_grads)), stream),
+              "step_inplace_ex")
 
 
 def step_backward(dtype, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, n, count, b1, b2, eps, eps_root,

@@ -724,6 +724,14 @@ int b200_adam_step_inplace(int dtype, int64_t num_leaves, void *const *p, void *
                                step_size, wd_l2, wd_decoupled, maximize, stream);
 }
 
+int b200_adam_step_inplace_ex(int dtype, int64_t num_leaves, void *const *p, void *const *g, void *const *mu,
+                              void *const *nu, const int64_t *n, const uint64_t *count, double b1, double b2,
+                              double eps, double eps_root, double step_size, double wd_l2, double wd_decoupled,
+                              int maximize, int overwrite_grads, void *stream) {
+  return step_forward_dispatch(true, dtype, num_leaves, p, g, mu, nu, p, mu, nu, overwrite_grads ? g : nullptr, n, count,
+                               b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, stream);
+}
+
 int b200_adam_step_backward(int dtype, int64_t num_leaves, const void *const *dp, const void *const *dus,
                             const void *const *new_mu, const void *const *new_nu, const void *const *g,
                             const void *const *dmu_ext, const void *const *dnu_ext, void *const *dg, void *const *dmu,

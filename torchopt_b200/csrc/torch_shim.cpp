@@ -352,7 +352,7 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>, std::v
     const std::vector<Tensor> &params, const std::vector<OptTensor> &grads, const std::vector<Tensor> &mu,
     const std::vector<Tensor> &nu, double b1, double b2, double eps, double eps_root, double step_size,
     const std::vector<size_t> &count, bool inplace, bool want_updates, double wd_l2, double wd_decoupled,
-    bool maximize) {
+    bool maximize, bool keep_grads = false) {
   const size_t L = params.size();
   if (grads.size() != L || mu.size() != L || nu.size() != L || count.size() != L)
     throw std::runtime_error("fused_step: params, grads, mu, nu and count must have the same number of leaves");
@@ -390,7 +390,8 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>, std::v
       const size_t i = idx[k];
       const Tensor &g = *grads[i];
       if (inplace) {
-        new_p[i] = params[i], new_mu[i] = mu[i], new_nu[i] = nu[i], new_us[i] = g;
+        new_p[i] = params[i], new_mu[i] = mu[i], new_nu[i] = nu[i];
+        if (!keep_grads) new_us[i] = g;   // reference side effect: the gradient tensor becomes the scaled update
       } else {
         new_p[i] = fa[per_leaf * k], new_mu[i] = fa[per_leaf * k + 1], new_nu[i] = fa[per_leaf * k + 2];
         if (want_updates) new_us[i] = fa[per_leaf * k + 3];
@@ -401,9 +402,11 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>, std::v
       n[k] = g.numel(), cnt[k] = count[i];
     }
     if (inplace) {
-      check(b200_adam_step_inplace(kv.first.dtype, (int64_t)G, op.data(), ous.data(), omu.data(), onu.data(), n.data(),
-                                   cnt.data(), b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize ? 1 : 0,
-                                   c.stream),
+      std::vector<void *> gio(G);
+      for (size_t k = 0; k < G; ++k) gio[k] = const_cast<void *>(pg[k]);
+      check(b200_adam_step_inplace_ex(kv.first.dtype, (int64_t)G, op.data(), gio.data(), omu.data(), onu.data(), n.data(),
+                                      cnt.data(), b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled,
+                                      maximize ? 1 : 0, keep_grads ? 0 : 1, c.stream),
             "fused_step (inplace)");
     } else {
       check(b200_adam_step_forward(kv.first.dtype, (int64_t)G, pp.data(), pg.data(), pmu.data(), pnu.data(), op.data(),
@@ -711,7 +714,7 @@ PYBIND11_MODULE(_C, mod) {
         py::arg("params"), py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("b1"), py::arg("b2"),
         py::arg("eps"), py::arg("eps_root"), py::arg("step_size"), py::arg("count"), py::arg("inplace") = false,
         py::arg("want_updates") = false, py::arg("wd_l2") = 0.0, py::arg("wd_decoupled") = 0.0,
-        py::arg("maximize") = false);
+        py::arg("maximize") = false, py::arg("keep_grads") = false);
   m.def("fused_step_backward", &fused_step_backward, "Backward of fused_step over all leaves (one launch)",
         py::arg("dparams"), py::arg("dscaled_updates"), py::arg("dmu_ext"), py::arg("dnu_ext"), py::arg("new_mu"),
         py::arg("new_nu"), py::arg("updates"), py::arg("need_dupdates"), py::arg("need_dmu"), py::arg("need_dnu"),

@@ -189,7 +189,8 @@ class FlatAdam:
     """In-place Adam whose parameters, gradients and moments live in four flat buffers (optim/adam.py +
     optim/base.py:99-124 re-laid-out).  ``p.data`` and ``p.grad`` of every parameter become views of ``flat_p`` /
     ``flat_g`` (values preserved), so ``loss.backward()`` accumulates straight into ``flat_g`` -- which is also the
-    all-reduce bucket for data-parallel training -- and ``step()`` is ONE single-range launch, 28 B/elem.
+    all-reduce bucket for data-parallel training -- and ``step()`` is ONE single-range launch, 28 B/elem (the gradients
+    are left as they are; the reference's in-place chain overwrites them with the updates).
 
     If some ``p.grad`` has been replaced (e.g. ``zero_grad(set_to_none=True)`` by foreign code followed by a fresh
     backward), ``step()`` first re-attaches the views and copies such gradients in; missing ones count as zero.
@@ -207,8 +208,10 @@ class FlatAdam:
         recipe = adamw if self.DECOUPLED else adam
         self.impl = recipe(lr, betas, eps, weight_decay, eps_root=eps_root, maximize=maximize,
                            use_accelerated_op=use_accelerated_op)
+        # the flat gradient buffer belongs to this optimizer (zero_grad clears it), so the reference's side effect of
+        # turning gradients into updates is not reproduced: the step writes p, mu, nu only -- 28 B/elem
         self.step_op = AdamStep(betas[0], betas[1], eps, eps_root=eps_root, step_size=-lr, weight_decay=weight_decay,
-                                decoupled=self.DECOUPLED, maximize=maximize, inplace=True)
+                                decoupled=self.DECOUPLED, maximize=maximize, inplace=True, keep_grads=True)
         self.layout = FlatLayout(self.params)
         with torch.no_grad():
             self.flat_p = self.layout.pack([p.detach() for p in self.params])
