@@ -163,3 +163,61 @@ def test_capture_after_eager_runs_and_no_garbage(path):
     torch.cuda.synchronize()
     for a, b, c in zip(got, want, kept):
         assert torch.equal(a, b) and torch.equal(a, c)
+
+
+@gpu
+def test_persistent_state_inside_a_capture_is_refused():
+    """Bias corrections are host scalars: a recorded step would replay with the step count of the recording.  Stepping a
+    state that was created outside the capture must therefore fail loudly instead of silently freezing the count."""
+    import torchopt_b200 as tb
+    dev = torch.device("cuda")
+    p = [torch.randn(1000, device=dev).requires_grad_(True)]
+    opt = tb.Adam(p, lr=1e-3)                     # persistent state, created eagerly
+    p[0].grad = torch.randn(1000, device=dev)
+    opt.step()                                     # eager steps are fine
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with pytest.raises(RuntimeError, match="OUTSIDE a CUDA-graph capture"):
+        with torch.cuda.graph(graph, stream=side):
+            opt.step()
+    torch.cuda.synchronize()
+    flat = tb.FlatAdam([torch.randn(64, device=dev).requires_grad_(True)], lr=1e-3)
+    graph2 = torch.cuda.CUDAGraph()
+    with pytest.raises(RuntimeError, match="OUTSIDE a CUDA-graph capture"):
+        with torch.cuda.graph(graph2, stream=side):
+            flat.step()
+    torch.cuda.synchronize()
+    opt.step()                                     # and the optimizer still works eagerly afterwards
+
+
+@gpu
+def test_capture_with_leaves_at_different_step_counts():
+    """A leaf that gets no gradient in the first inner step has a different step count afterwards; the counters are
+    then built by fills (not by a host->device copy, which must not be recorded) and the replay matches eager."""
+    import torchopt_b200 as tb
+    dev = torch.device("cuda")
+    torch.manual_seed(9)
+    sizes = [100, 2000, 33]
+    params = [(torch.randn(k, device=dev) * 0.2).requires_grad_(True) for k in sizes]
+
+    def fn(w):
+        opt = tb.FuncAdam(1e-2, eps_root=1e-8)
+        cur = list(params)
+        for k in range(3):
+            grads = [w[: p.numel()] * p for p in cur]
+            if k == 0:
+                grads[1] = None
+            cur = opt.apply_gradients(grads, cur)
+        st = next(s for s in opt.state if isinstance(s, tb.ScaleByAdamState))
+        assert [int(c._b200_host_count) for c in st.count] == [3, 2, 3]
+        return torch.autograd.grad(torch.stack([(p * p).sum() for p in cur]).sum(), params)
+
+    w0 = torch.rand(2000, device=dev) + 0.5
+    step = tb.graphs.capture(fn, w0)
+    w1 = torch.rand(2000, device=dev) + 0.25
+    want = fn(w1)
+    got = step(w1)
+    torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)

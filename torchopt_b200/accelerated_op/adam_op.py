@@ -32,12 +32,32 @@ INT64_MAX = torch.iinfo(torch.int64).max
 NATIVE_NODE = os.environ.get("B200_ADAM_PY_NODES", "") in ("", "0")
 
 
-def tag_count(count: torch.Tensor, host: int) -> torch.Tensor:
+def capturing() -> bool:
+    """True while the current CUDA stream is recording a CUDA graph."""
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
+def tag_count(count: torch.Tensor, host: int, in_capture: bool | None = None) -> torch.Tensor:
     """Attach the host mirror of a step counter to its device tensor, together with the tensor's version so that an
-    in-place edit of the counter (which bumps the version) invalidates the mirror."""
+    in-place edit of the counter (which bumps the version) invalidates the mirror, and with whether the counter was
+    created while a CUDA graph was being recorded (see ``check_capturable``)."""
     count._b200_host_count = host  # type: ignore[attr-defined]
     count._b200_host_version = count._version  # type: ignore[attr-defined]
+    count._b200_in_capture = capturing() if in_capture is None else in_capture  # type: ignore[attr-defined]
     return count
+
+
+def check_capturable(count: Any) -> None:
+    """Bias corrections are host scalars baked into the launch, so a recorded step replays with the step count it was
+    recorded at.  That is right when the optimizer state is created inside the recorded function (a task's inner loop
+    always counts 1..K from a fresh state) and silently WRONG when a persistent state is stepped inside a capture
+    (e.g. a recorded training iteration around ``Adam.step()``): refuse the latter."""
+    if isinstance(count, torch.Tensor) and not getattr(count, "_b200_in_capture", True) and capturing():
+        raise RuntimeError(
+            "torchopt_b200: an optimizer state created OUTSIDE a CUDA-graph capture is being stepped INSIDE one. The "
+            "bias corrections 1/(1-b^count) are host scalars, so every replay would reuse the step count of the "
+            "recording. Create the state inside the captured function (fresh state per replay, as in a MAML inner "
+            "loop), or keep optimizer steps with persistent state outside the graph.")
 
 
 def count_as_int(count: Any) -> int:

@@ -21,6 +21,10 @@ Why this works for the Adam path without special cases:
 * ``GradBucket`` keeps every ``.grad`` a view of one static buffer, so the captured ``backward()`` accumulates in
   place into memory the caller can read, all-reduce and zero between replays.
 
+What is NOT capturable: stepping an optimizer whose state lives across replays (e.g. a recorded training iteration
+around ``Adam.step()``) -- the recorded bias corrections would be those of the recording step.  That case raises
+(``accelerated_op.adam_op.check_capturable``) instead of replaying wrong numbers.
+
 Python side effects of ``fn`` (building optimizer objects, re-binding module parameters) run during warm-up and
 capture only; a replay re-executes the recorded GPU work on the static inputs and nothing else.
 """

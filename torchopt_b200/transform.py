@@ -19,7 +19,8 @@ from typing import Any, Callable, NamedTuple, Sequence
 import torch
 
 from torchopt_b200 import _pytree
-from torchopt_b200.accelerated_op.adam_op import INT64_MAX, AdamOp, count_as_int, tag_count
+from torchopt_b200.accelerated_op.adam_op import (INT64_MAX, AdamOp, capturing, check_capturable, count_as_int,
+                                                    tag_count)
 
 
 # A/B switch for parity tests: False routes the differentiable path through the reference's three-node graph
@@ -55,6 +56,7 @@ def make_counts(values: Sequence[int | None], devices: Sequence[torch.device | N
     produced by one fill kernel; otherwise by one small host->device copy."""
     out: list = [None] * len(values)
     by_dev: dict = {}
+    in_capture = capturing()
     for i, (v, d) in enumerate(zip(values, devices)):
         if v is not None:
             by_dev.setdefault(d, []).append(i)
@@ -62,6 +64,18 @@ def make_counts(values: Sequence[int | None], devices: Sequence[torch.device | N
         vals = [values[i] for i in idx]
         if all(v == vals[0] for v in vals):
             vec = torch.full((len(idx),), vals[0], dtype=torch.int64, device=dev)
+        elif in_capture:
+            # a host->device copy from a temporary pinned buffer must not be recorded (the buffer is gone at replay):
+            # one fill per distinct value instead
+            vec = torch.empty((len(idx),), dtype=torch.int64, device=dev)
+            for v in sorted(set(vals)):
+                sel = [k for k, x in enumerate(vals) if x == v]
+                lo, hi = sel[0], sel[-1] + 1
+                if sel == list(range(lo, hi)):
+                    vec[lo:hi].fill_(v)
+                else:
+                    for k in sel:
+                        vec[k].fill_(v)
         else:
             host = torch.tensor(vals, dtype=torch.int64)
             if dev.type == "cuda" and torch.cuda.is_available():
@@ -69,7 +83,7 @@ def make_counts(values: Sequence[int | None], devices: Sequence[torch.device | N
             else:
                 vec = host.to(dev)
         for i, view in zip(idx, vec.unbind(0)):
-            out[i] = _tag(view, values[i])
+            out[i] = _tag(view, values[i], in_capture)
     return out
 
 
@@ -109,10 +123,14 @@ def inc_count_flat(updates: Sequence, counts: Sequence) -> list:
     """``count + 1`` (saturating at INT64_MAX) for leaves that received an update; others pass through.
     Same values as transform/utils.py:111-122, built from the host mirrors."""
     values, devices = [], []
+    checked = False
     for g, c in zip(updates, counts):
         if g is None or c is None:
             values.append(None), devices.append(None)
             continue
+        if not checked:          # one counter speaks for the state (they are created together)
+            check_capturable(c)
+            checked = True
         host = count_as_int(c)   # tags an untagged / edited counter after reading it once
         values.append(host + (host != INT64_MAX))
         devices.append(c.device if isinstance(c, torch.Tensor) else torch.device("cpu"))
