@@ -163,6 +163,24 @@ int b200_adam_step_inplace_ex(int dtype, int64_t num_leaves, void *const *p, voi
                               double eps, double eps_root, double step_size, double wd_l2, double wd_decoupled,
                               int maximize, int overwrite_grads, void *stream);
 
+/* Capturable in-place step: for an optimizer step that is recorded in a CUDA graph together with the rest of a training
+ * iteration (the reference cannot be recorded at all: its binding reads `count` back to the host on every call,
+ * accelerated_op/adam_op.py:98-101).  Nothing about the step count is baked into the launch:
+ *   count_dev[i]   DEVICE pointer to the int64 step count of leaf i, already incremented by the caller on the device;
+ *   c1/c2_table    DEVICE arrays of `table_len` bias corrections 1/(1-b^count) for count = 1..table_len in the
+ *                  arithmetic type (float for F32 and BF16_F32, double for F64), produced on the host by
+ *                  b200_adam_bias_table -- the same std::pow expression and single rounding as every other entry point,
+ *                  hence bit-identical results.  b200_adam_bias_table_len gives the length after which both corrections
+ *                  are exactly 1 (16 628 entries for b2 = 0.999 in fp32); larger counts use the last entry.
+ * Otherwise identical to b200_adam_step_inplace_ex. */
+int64_t b200_adam_bias_table_len(int dtype, double b1, double b2);
+int b200_adam_bias_table(int dtype, double b1, double b2, int64_t len, void *c1_host, void *c2_host);
+int b200_adam_step_inplace_capturable(int dtype, int64_t num_leaves, void *const *p, void *const *g, void *const *mu,
+                                      void *const *nu, const int64_t *n, const int64_t *const *count_dev,
+                                      const void *c1_table_dev, const void *c2_table_dev, int64_t table_len, double b1,
+                                      double b2, double eps, double eps_root, double step_size, double wd_l2,
+                                      double wd_decoupled, int maximize, int overwrite_grads, void *stream);
+
 /* Backward of b200_adam_step_forward.  Incoming per leaf (each may be NULL): dp = gradient of p_out, dus = gradient of
  * us_out (the array argument itself may be NULL), dmu_ext / dnu_ext = gradients of mu_out / nu_out.
  *   du2 = (dp + dus) * step_size ; then exactly b200_adam_fused_backward with u recomputed from new_mu, new_nu and the

@@ -1,0 +1,156 @@
+"""Capturable in-place Adam (`Adam(..., capturable=True)`, `FlatAdam(..., capturable=True)`,
+`b200_adam_step_inplace_capturable`): step counts on the device, bias corrections from host-computed tables.
+Must be bit-identical to the host-scalar path at every step count -- inside the tables, at their last entry and far
+beyond it -- and a training iteration recorded in a CUDA graph must advance the optimizer by one real step per replay."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal
+
+torch = pytest.importorskip("torch")
+from torch import nn  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+SIZES = [5, 64, 321, 4097, 36_864]
+
+
+def test_bias_tables_match_the_reference_expression():
+    """The tables hold float(1 / (1 - pow(b, count))) -- the reference launchers' host expression
+    (adam_op_impl_cuda.cu:73-75) -- for count = 1..len, and end exactly where both corrections have become 1."""
+    import math
+
+    import torchopt_b200 as tb
+    for family, dt in ((0, np.float32), (1, np.float64)):
+        for b1, b2 in ((0.9, 0.999), (0.5, 0.6), (0.0, 0.3)):
+            c1, c2 = (t.numpy() for t in tb.adam_op.bias_tables(family, b1, b2))
+            n = len(c1)
+            want1 = np.array([dt(1 / (1 - math.pow(b1, c))) for c in range(1, n + 1)], dtype=dt)
+            want2 = np.array([dt(1 / (1 - math.pow(b2, c))) for c in range(1, n + 1)], dtype=dt)
+            assert_bits_equal(c1, want1, "c1 table")
+            assert_bits_equal(c2, want2, "c2 table")
+            assert c1[-1] == 1 and c2[-1] == 1 and (n == 1 or c1[-2] != 1 or c2[-2] != 1)
+            for c in (n + 1, 10 * n, 10**9):
+                assert dt(1 / (1 - math.pow(b1, c))) == 1 and dt(1 / (1 - math.pow(b2, c))) == 1
+    with pytest.raises(RuntimeError, match="2\\^24"):
+        tb.adam_op.bias_tables(0, 0.9, 0.9999999)
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_capturable_abi_vs_oracle_at_any_count(c_oracle, tag):
+    """Raw C ABI: device count + tables vs the oracle's whole-step composition, for counts inside the table, at its end
+    and far beyond it; gradients overwritten or left alone."""
+    from oracle import adam_oracle as ao
+    from torchopt_b200 import abi
+    import torchopt_b200 as tb
+    dt, npdt = (abi.F32, np.float32) if tag == "f32" else (abi.F64, np.float64)
+    b1, b2, eps, er, lr = 0.9, 0.999, 1e-8, 1e-8, 3e-3
+    c1, c2 = (t.cuda() for t in tb.adam_op.bias_tables(1 if tag == "f64" else 0, b1, b2))
+    T = c1.numel()
+    rng = np.random.default_rng(5)
+    s = torch.cuda.current_stream().cuda_stream
+    lib = abi.load()
+    for n in (1, 1023, 70_001):
+        p = (rng.standard_normal(n) * 0.3).astype(npdt)
+        g = (rng.standard_normal(n) * 1e-2).astype(npdt)
+        mu = (rng.standard_normal(n) * 1e-2).astype(npdt)
+        nu = (rng.random(n) * 1e-4).astype(npdt)
+        for count in (1, 7, T - 1, T, T + 1, 10**6, 2**40):
+            w_p, w_mu, w_nu, w_us = ao.fused_step_forward(c_oracle, p, g, mu, nu, b1, b2, eps, er, count, -lr)
+            for overwrite in (0, 1):
+                P, G, MU, NU = (torch.from_numpy(a.copy()).cuda() for a in (p, g, mu, nu))
+                cnt = torch.tensor(count, dtype=torch.int64, device="cuda")
+                rc = lib.b200_adam_step_inplace_capturable(
+                    dt, 1, abi._ptrs([P.data_ptr()]), abi._ptrs([G.data_ptr()]), abi._ptrs([MU.data_ptr()]),
+                    abi._ptrs([NU.data_ptr()]), abi._arr(abi.c_int64, [n]), abi._ptrs([cnt.data_ptr()]), c1.data_ptr(),
+                    c2.data_ptr(), T, b1, b2, eps, er, -lr, 0.0, 0.0, 0, overwrite, s)
+                assert rc == 0
+                torch.cuda.synchronize()
+                what = f"capturable n={n} count={count} overwrite={overwrite}"
+                assert_bits_equal(P.cpu().numpy(), w_p, what + " p")
+                assert_bits_equal(MU.cpu().numpy(), w_mu, what + " mu")
+                assert_bits_equal(NU.cpu().numpy(), w_nu, what + " nu")
+                assert_bits_equal(G.cpu().numpy(), w_us if overwrite else g, what + " g")
+
+
+class Elementwise(nn.Module):
+    def __init__(self, sizes, dtype=torch.float32):
+        super().__init__()
+        self.ps = nn.ParameterList([nn.Parameter((torch.randn(k, device="cuda") * 0.3).to(dtype)) for k in sizes])
+
+    def forward(self, ws):
+        return torch.stack([(w * p * p).sum() for w, p in zip(ws, self.ps)]).sum()
+
+
+@pytest.mark.parametrize("cls_name,dtype,betas,steps", [
+    ("FlatAdam", torch.float32, (0.5, 0.6), 45),        # table of 33 entries: crossed during the run
+    ("FlatAdamW", torch.float32, (0.9, 0.999), 12),
+    ("Adam", torch.float32, (0.5, 0.6), 45),
+    ("AdamW", torch.float64, (0.9, 0.999), 8),
+    ("FlatAdam", torch.bfloat16, (0.9, 0.999), 8),
+])
+def test_capturable_equals_host_scalar_path_eagerly(cls_name, dtype, betas, steps):
+    import torchopt_b200 as tb
+    torch.manual_seed(11)
+    net_a, net_b = Elementwise(SIZES, dtype), Elementwise(SIZES, dtype)
+    net_b.load_state_dict(net_a.state_dict())
+    cls = getattr(tb, cls_name)
+    kw = dict(lr=1e-2, betas=betas, eps_root=1e-8, weight_decay=0.01)
+    opt_a, opt_b = cls(net_a.parameters(), **kw), cls(net_b.parameters(), capturable=True, **kw)
+    ws = [(torch.rand(k, device="cuda") + 0.5).to(dtype) for k in SIZES]
+    for k in range(steps):
+        for net, opt in ((net_a, opt_a), (net_b, opt_b)):
+            opt.zero_grad()
+            net(ws).backward()
+            if cls_name in ("Adam", "AdamW") and k % 5 == 1:
+                list(net.parameters())[2].grad = None          # a leaf that skips this step: its count stays behind
+            opt.step()
+        for p, q in zip(net_a.parameters(), net_b.parameters()):
+            assert torch.equal(p, q), f"step {k}"
+    st = next(s for s in opt_b.state if isinstance(s, tb.ScaleByAdamState))
+    counts = [int(c) for c in st.count]
+    if cls_name in ("Adam", "AdamW"):
+        skipped = len([k for k in range(steps) if k % 5 == 1])
+        assert counts == [steps, steps, steps - skipped, steps, steps]
+    else:
+        assert counts == [steps]
+
+
+@pytest.mark.parametrize("flat", [True, False])
+def test_training_iteration_recorded_in_a_cuda_graph(flat):
+    """zero_grad + forward + backward + optimizer step in ONE graph: N replays == N eager iterations, bit for bit."""
+    import torchopt_b200 as tb
+    torch.manual_seed(12)
+    net_a, net_b = Elementwise(SIZES), Elementwise(SIZES)
+    net_b.load_state_dict(net_a.state_dict())
+    cls = tb.FlatAdam if flat else tb.Adam
+    kw = dict(lr=1e-2, betas=(0.7, 0.8), eps_root=1e-8)
+    opt_a, opt_b = cls(net_a.parameters(), **kw), cls(net_b.parameters(), capturable=True, **kw)
+    w = [torch.rand(k, device="cuda") + 0.5 for k in SIZES]
+
+    def iteration(net, opt, ws):
+        opt.zero_grad()
+        loss = net(ws)
+        loss.backward()
+        opt.step()
+        return loss.detach()
+
+    warmup, replays = 2, 9
+    step = tb.graphs.capture(lambda *ws: iteration(net_b, opt_b, ws), *w, warmup=warmup)
+    losses_b = [step().clone() for _ in range(replays)]
+    losses_a = [iteration(net_a, opt_a, w) for _ in range(warmup + replays)]
+    torch.cuda.synchronize()
+    for p, q in zip(net_a.parameters(), net_b.parameters()):
+        assert torch.equal(p, q)
+    for a, b in zip(losses_a[warmup:], losses_b):
+        assert torch.equal(a, b)
+    st = next(s for s in opt_b.state if isinstance(s, tb.ScaleByAdamState))
+    assert all(int(c) == warmup + replays for c in st.count)
+    # new data through the static input slots
+    w2 = [torch.rand(k, device="cuda") + 0.25 for k in SIZES]
+    lb = step(*w2).clone()
+    la = iteration(net_a, opt_a, w2)
+    assert torch.equal(la, lb)
+    for p, q in zip(net_a.parameters(), net_b.parameters()):
+        assert torch.equal(p, q)

@@ -57,7 +57,8 @@ def check_capturable(count: Any) -> None:
             "torchopt_b200: an optimizer state created OUTSIDE a CUDA-graph capture is being stepped INSIDE one. The "
             "bias corrections 1/(1-b^count) are host scalars, so every replay would reuse the step count of the "
             "recording. Create the state inside the captured function (fresh state per replay, as in a MAML inner "
-            "loop), or keep optimizer steps with persistent state outside the graph.")
+            "loop), or -- for an in-place training step -- build the optimizer with capturable=True (Adam / AdamW / "
+            "FlatAdam / FlatAdamW), which keeps the step count on the device.")
 
 
 def count_as_int(count: Any) -> int:

@@ -509,6 +509,32 @@ struct StepFwd {
   }
 };
 
+// Capturable in-place step (for an optimizer step recorded in a CUDA graph together with the forward / backward of a
+// training iteration): nothing about the step count may be baked into the launch, so
+//   * the count is read from DEVICE memory (ptr[8]: const int64*, incremented on the device by the caller), and
+//   * the bias corrections C1 = 1/(1-b1^count), C2 = 1/(1-b2^count) come from device TABLES (ptr[9], ptr[10]) indexed by
+//     count.  The tables are filled on the host with the very expressions the other launchers use (std::pow in double,
+//     one rounding to CT), so results stay bit-identical to the host-scalar path; they end where both corrections have
+//     become exactly 1 in CT (count 16 628 for b2 = 0.999 in fp32), and larger counts clamp to the last entry.
+// `flags` of the table carries the table length.
+template <typename TG_, typename TS_, typename CT_>
+struct StepFwdCap : StepFwd<TG_, TS_, CT_, true> {
+  using Base = StepFwd<TG_, TS_, CT_, true>;
+  using CT = CT_;
+  using Leaf = typename Base::Leaf;
+  static constexpr int NPTR = 11;
+  template <class Tab>
+  static __device__ __forceinline__ Leaf leaf(const Tab &t, int l) {
+    Leaf L = Base::leaf(t, l);
+    const long long c = *(const long long *)t.ptr[8][l];
+    const int len = t.flags;
+    const int idx = c < 1 ? 0 : (c > (long long)len ? len - 1 : (int)c - 1);
+    L.C1 = ((const CT *)t.ptr[9][l])[idx];
+    L.C2 = ((const CT *)t.ptr[10][l])[idx];
+    return L;
+  }
+};
+
 // backward of the whole step.  Incoming: dp' (gradient of the new parameters), dmu_ext, dnu_ext (gradients of the new
 // moments from later steps) and optionally dus (gradient of the returned scaled update, normally absent).
 //   du_s  = dp' (+ dus)            AddBackward of p' = p + us: both inputs receive dp'      (dp = dp' is returned by

@@ -361,6 +361,14 @@ struct StepFwdH : StepFwd<TG, TS, CT, INPLACE> {
       if (p[a]) p[a] = (char *)p[a] + (size_t)k * sz[a];
   }
 };
+template <typename TG, typename TS, typename CT>
+struct StepFwdCapH : StepFwdCap<TG, TS, CT> {
+  static void advance(void **p, long long k) {  // the count pointer and the two tables (8..10) do not move
+    const size_t sz[8] = {sizeof(TG), sizeof(TG), sizeof(TS), sizeof(TS), sizeof(TG), sizeof(TS), sizeof(TS), sizeof(TG)};
+    for (int a = 0; a < 8; ++a)
+      if (p[a]) p[a] = (char *)p[a] + (size_t)k * sz[a];
+  }
+};
 template <typename TG, typename TS, typename CT, int MODE>
 struct StepBwdH : StepBwd<TG, TS, CT, MODE> {
   static void advance(void **p, long long k) {
@@ -406,6 +414,50 @@ static int step_forward_impl(int64_t L, const void *const *p, const void *const 
   };
   using C = Cfg<TG, TS>;
   return run_op<Op, C::P_FWD, C::U_FWD>(L, total, 0, gs, next, stream);
+}
+
+template <typename TG, typename TS, typename T>
+static int step_capturable_impl(int64_t L, void *const *p, void *const *g, void *const *mu, void *const *nu,
+                                const int64_t *n, const int64_t *const *count_dev, const void *c1_table,
+                                const void *c2_table, int64_t table_len, double b1, double b2, double eps,
+                                double eps_root, double step_size, double wd_l2, double wd_decoupled, int maximize,
+                                int overwrite_grads, cudaStream_t stream) {
+  using Op = StepFwdCapH<TG, TS, T>;
+  const T B1 = (T)b1, B2 = (T)b2;
+  const T gs[10] = {B1, T(1) - B1, B2, T(1) - B2, (T)eps_root, (T)eps, (T)step_size, (T)wd_l2, (T)wd_decoupled,
+                    maximize ? T(-1) : T(1)};
+  long long total = 0;
+  for (int64_t i = 0; i < L; ++i) {
+    if (n[i] < 0) return B200_ADAM_E_ARG;
+    if (n[i] > 0 && (!p[i] || !g[i] || !mu[i] || !nu[i] || !count_dev[i])) return B200_ADAM_E_ARG;
+    total += n[i];
+  }
+  auto next = [&](long long i, HostLeaf<Op> &hl) {
+    if (n[i] == 0) return false;
+    hl.ptr[0] = p[i], hl.ptr[1] = g[i], hl.ptr[2] = mu[i], hl.ptr[3] = nu[i];
+    hl.ptr[4] = p[i], hl.ptr[5] = mu[i], hl.ptr[6] = nu[i], hl.ptr[7] = overwrite_grads ? g[i] : nullptr;
+    hl.ptr[8] = const_cast<int64_t *>(count_dev[i]);
+    hl.ptr[9] = const_cast<void *>(c1_table), hl.ptr[10] = const_cast<void *>(c2_table);
+    hl.n = n[i];
+    hl.ls[0] = T(0), hl.ls[1] = T(0);  // unused: the corrections come from the device tables
+    return true;
+  };
+  using C = Cfg<TG, TS>;
+  return run_op<Op, C::P_FWD, C::U_FWD>(L, total, (int)table_len, gs, next, stream);
+}
+
+// number of table entries after which 1/(1-b^count) is exactly 1 in T for every larger count (the value decreases
+// monotonically to 1); 0 if that does not happen within `cap` counts
+template <typename T>
+static int64_t bias_table_len_one(double b, int64_t cap) {
+  auto is_one = [&](int64_t c) { return (T)inv_one_minus_pow(b, (uint64_t)c) == T(1); };
+  if (!is_one(cap)) return 0;
+  int64_t lo = 1, hi = cap;  // smallest c with is_one(c)
+  while (lo < hi) {
+    const int64_t mid = lo + (hi - lo) / 2;
+    if (is_one(mid)) hi = mid; else lo = mid + 1;
+  }
+  return lo;
 }
 
 template <typename TG, typename TS, typename T, int MODE>
@@ -730,6 +782,65 @@ int b200_adam_step_inplace_ex(int dtype, int64_t num_leaves, void *const *p, voi
                               int maximize, int overwrite_grads, void *stream) {
   return step_forward_dispatch(true, dtype, num_leaves, p, g, mu, nu, p, mu, nu, overwrite_grads ? g : nullptr, n, count,
                                b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, stream);
+}
+
+int64_t b200_adam_bias_table_len(int dtype, double b1, double b2) {
+  if (!(b1 >= 0.0 && b1 < 1.0 && b2 >= 0.0 && b2 < 1.0)) return B200_ADAM_E_ARG;
+  const int64_t cap = int64_t(1) << 24;
+  int64_t a, b;
+  if (dtype == B200_ADAM_F64) {
+    a = bias_table_len_one<double>(b1, cap), b = bias_table_len_one<double>(b2, cap);
+  } else if (dtype == B200_ADAM_F32 || dtype == B200_ADAM_BF16_F32) {
+    a = bias_table_len_one<float>(b1, cap), b = bias_table_len_one<float>(b2, cap);
+  } else {
+    return B200_ADAM_E_DTYPE;
+  }
+  if (a == 0 || b == 0) return B200_ADAM_E_ARG;  // a beta so close to 1 that the table would exceed 2^24 entries
+  return a > b ? a : b;
+}
+
+int b200_adam_bias_table(int dtype, double b1, double b2, int64_t len, void *c1_host, void *c2_host) {
+  if (len <= 0 || !c1_host || !c2_host) return B200_ADAM_E_ARG;
+  if (dtype == B200_ADAM_F64) {
+    for (int64_t c = 1; c <= len; ++c) {
+      ((double *)c1_host)[c - 1] = inv_one_minus_pow(b1, (uint64_t)c);
+      ((double *)c2_host)[c - 1] = inv_one_minus_pow(b2, (uint64_t)c);
+    }
+    return 0;
+  }
+  if (dtype == B200_ADAM_F32 || dtype == B200_ADAM_BF16_F32) {
+    for (int64_t c = 1; c <= len; ++c) {
+      ((float *)c1_host)[c - 1] = (float)inv_one_minus_pow(b1, (uint64_t)c);
+      ((float *)c2_host)[c - 1] = (float)inv_one_minus_pow(b2, (uint64_t)c);
+    }
+    return 0;
+  }
+  return B200_ADAM_E_DTYPE;
+}
+
+int b200_adam_step_inplace_capturable(int dtype, int64_t num_leaves, void *const *p, void *const *g, void *const *mu,
+                                      void *const *nu, const int64_t *n, const int64_t *const *count_dev,
+                                      const void *c1_table_dev, const void *c2_table_dev, int64_t table_len, double b1,
+                                      double b2, double eps, double eps_root, double step_size, double wd_l2,
+                                      double wd_decoupled, int maximize, int overwrite_grads, void *stream) {
+  if (num_leaves < 0) return B200_ADAM_E_ARG;
+  if (num_leaves == 0) return 0;
+  if (!p || !g || !mu || !nu || !n || !count_dev || !c1_table_dev || !c2_table_dev || table_len <= 0 ||
+      table_len > (int64_t(1) << 24))
+    return B200_ADAM_E_ARG;
+  if (wd_l2 != 0.0 && wd_decoupled != 0.0) return B200_ADAM_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+#define B200_STEP_CAP(TG, TS, CT)                                                                                     \
+  return step_capturable_impl<TG, TS, CT>(num_leaves, p, g, mu, nu, n, count_dev, c1_table_dev, c2_table_dev, table_len, \
+                                          b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize,              \
+                                          overwrite_grads, s)
+#ifndef B200_ADAM_TUNE_F32_ONLY
+  if (dtype == B200_ADAM_F64) B200_STEP_CAP(double, double, double);
+  if (dtype == B200_ADAM_BF16_F32) B200_STEP_CAP(bf16_t, float, float);
+#endif
+  if (dtype == B200_ADAM_F32) B200_STEP_CAP(float, float, float);
+#undef B200_STEP_CAP
+  return B200_ADAM_E_DTYPE;
 }
 
 int b200_adam_step_backward(int dtype, int64_t num_leaves, const void *const *dp, const void *const *dus,

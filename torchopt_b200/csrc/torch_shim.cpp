@@ -500,6 +500,57 @@ fused_step_backward(
   return {dg, dmu, dnu, dp};
 }
 
+// ---- capturable in-place step (device-resident step counts + host-computed bias-correction tables) -------------
+// (c1_table, c2_table) on the CPU for a dtype family: 0 = float32 tables (fp32 and bf16-param/fp32-state), 1 = float64
+std::tuple<Tensor, Tensor> bias_tables(int dtype_family, double b1, double b2) {
+  const int64_t len = b200_adam_bias_table_len(dtype_family, b1, b2);
+  if (len <= 0)
+    throw std::runtime_error("bias_tables: betas this close to 1 need more than 2^24 table entries; not capturable");
+  auto opts = at::TensorOptions().dtype(dtype_family == B200_ADAM_F64 ? at::kDouble : at::kFloat).device(at::kCPU);
+  Tensor c1 = at::empty({len}, opts), c2 = at::empty({len}, opts);
+  check(b200_adam_bias_table(dtype_family, b1, b2, len, c1.data_ptr(), c2.data_ptr()), "bias_tables");
+  return {c1, c2};
+}
+
+// In-place Adam step over all leaves whose step counts live on the DEVICE (0-dim int64 CUDA tensors, already
+// incremented) -- safe to record in a CUDA graph.  Leaves must share one device and one dtype family.
+void fused_step_capturable(const std::vector<Tensor> &params, const std::vector<Tensor> &grads,
+                           const std::vector<Tensor> &mu, const std::vector<Tensor> &nu,
+                           const std::vector<Tensor> &count, const Tensor &c1_table, const Tensor &c2_table, double b1,
+                           double b2, double eps, double eps_root, double step_size, double wd_l2, double wd_decoupled,
+                           bool maximize, bool keep_grads) {
+  const size_t L = params.size();
+  if (L == 0) return;
+  if (grads.size() != L || mu.size() != L || nu.size() != L || count.size() != L)
+    throw std::runtime_error("fused_step_capturable: params, grads, mu, nu and count must have the same number of leaves");
+  require_cuda(params[0]);
+  const int dt = family(grads[0], mu[0], "adamStepCUDA", true);
+  const auto table_type = dt == B200_ADAM_F64 ? at::kDouble : at::kFloat;
+  if (c1_table.scalar_type() != table_type || c2_table.scalar_type() != table_type || !c1_table.is_cuda() ||
+      !c2_table.is_cuda() || !c1_table.is_contiguous() || !c2_table.is_contiguous() ||
+      c1_table.numel() != c2_table.numel() || c1_table.numel() == 0)
+    throw std::runtime_error("fused_step_capturable: bias tables must be contiguous CUDA tensors of the arithmetic type");
+  std::vector<void *> pp(L), pg(L), pmu(L), pnu(L);
+  std::vector<const int64_t *> pc(L);
+  std::vector<int64_t> n(L);
+  for (size_t i = 0; i < L; ++i) {
+    require_cuda(params[i]);
+    if (family(grads[i], mu[i], "adamStepCUDA", true) != dt || params[i].device() != params[0].device())
+      throw std::runtime_error("fused_step_capturable: all leaves must share one device and one dtype family");
+    same_type(mu[i], nu[i]), same_type(grads[i], params[i]);
+    if (!count[i].is_cuda() || count[i].scalar_type() != at::kLong || count[i].numel() != 1)
+      throw std::runtime_error("fused_step_capturable: step counts must be one-element int64 CUDA tensors");
+    pp[i] = params[i].data_ptr(), pg[i] = grads[i].data_ptr(), pmu[i] = mu[i].data_ptr(), pnu[i] = nu[i].data_ptr();
+    pc[i] = count[i].data_ptr<int64_t>(), n[i] = grads[i].numel();
+  }
+  Ctx c(params[0]);
+  check(b200_adam_step_inplace_capturable(dt, (int64_t)L, pp.data(), pg.data(), pmu.data(), pnu.data(), n.data(),
+                                          pc.data(), c1_table.data_ptr(), c2_table.data_ptr(), c1_table.numel(), b1, b2,
+                                          eps, eps_root, step_size, wd_l2, wd_decoupled, maximize ? 1 : 0,
+                                          keep_grads ? 0 : 1, c.stream),
+        "fused_step_capturable");
+}
+
 // ---- native autograd nodes ----------------------------------------------------------------------------
 // The Python autograd.Function wrappers (accelerated_op/adam_op.py:FusedOp, adam_step.py:AdamStep.Op) spend ~200 us per
 // call on a 62-leaf pytree in THPFunction bookkeeping (248 inputs / 186 outputs), 3x the launch itself.  These C++
@@ -721,6 +772,14 @@ PYBIND11_MODULE(_C, mod) {
         py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("step_size"), py::arg("count"),
         py::arg("params"), py::arg("need_dparams"), py::arg("wd_l2") = 0.0, py::arg("wd_decoupled") = 0.0,
         py::arg("maximize") = false);
+  m.def("bias_tables", &bias_tables, "host-computed bias-correction tables (c1, c2) for the capturable step",
+        py::arg("dtype_family"), py::arg("b1"), py::arg("b2"));
+  m.def("fused_step_capturable", &fused_step_capturable,
+        "in-place Adam step with device-resident step counts (recordable in a CUDA graph)", py::arg("params"),
+        py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("count"), py::arg("c1_table"), py::arg("c2_table"),
+        py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("step_size"),
+        py::arg("wd_l2") = 0.0, py::arg("wd_decoupled") = 0.0, py::arg("maximize") = false,
+        py::arg("keep_grads") = false);
   m.def("fused_autograd", &fused_autograd,
         "fused_forward as ONE native autograd node (backward = fused_backward): returns mu'.., nu'.., u..",
         py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("b1"), py::arg("b2"), py::arg("eps"),

@@ -26,7 +26,7 @@ import torch
 from torch import nn
 
 from torchopt_b200.accelerated_op.adam_step import AdamStep
-from torchopt_b200.optim import _fused_chain_step, adam, adamw
+from torchopt_b200.optim import CapturableCounts, _capturable_step, _fused_chain_step, adam, adamw
 from torchopt_b200.transform import ScaleByAdamState
 
 __all__ = ["FlatLayout", "FlatMetaAdam", "FlatMetaAdamW", "FlatAdam", "FlatAdamW"]
@@ -201,7 +201,9 @@ class FlatAdam:
     # pylint: disable-next=too-many-arguments
     def __init__(self, params: Iterable[torch.Tensor], lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 0.0, *, eps_root: float = 0.0, maximize: bool = False,
-                 use_accelerated_op: bool = True) -> None:
+                 use_accelerated_op: bool = True, capturable: bool = False) -> None:
+        """``capturable=True``: the step count lives on the device, so ``step()`` can be recorded in a CUDA graph with
+        the rest of a training iteration (``zero_grad`` + forward + backward + ``step``); each replay is a real step."""
         if callable(lr):
             raise NotImplementedError("learning-rate schedules are outside the scope of torchopt_b200")
         self.params = list(params)
@@ -224,6 +226,13 @@ class FlatAdam:
             p.data = pv
             p.grad = gv
         self.state = self.impl.init([self.flat_p])
+        self.capturable = None
+        if capturable:
+            self.capturable = CapturableCounts([self.flat_p], betas[0], betas[1])
+            k = next(i for i, st in enumerate(self.state) if isinstance(st, ScaleByAdamState))
+            st = self.state[k]
+            self.state = (*self.state[:k], ScaleByAdamState(mu=st.mu, nu=st.nu, count=self.capturable.counts),
+                          *self.state[k + 1:])
 
     def zero_grad(self, set_to_none: bool = False) -> None:  # noqa: ARG002  the flat buffer is never dropped
         """One memset of the flat gradient buffer; the ``.grad`` views stay attached."""
@@ -244,6 +253,10 @@ class FlatAdam:
     @torch.no_grad()
     def step(self) -> None:
         self._gather_foreign_grads()
+        if self.capturable is not None:
+            st = next(s for s in self.state if isinstance(s, ScaleByAdamState))
+            _capturable_step(self.step_op, self.capturable, [self.flat_p], [self.flat_g], st)
+            return
         _, self.state = _fused_chain_step(self.step_op, [self.flat_p], [self.flat_g], self.state)
 
     def state_dict(self) -> ScaleByAdamState:

@@ -21,9 +21,11 @@ Why this works for the Adam path without special cases:
 * ``GradBucket`` keeps every ``.grad`` a view of one static buffer, so the captured ``backward()`` accumulates in
   place into memory the caller can read, all-reduce and zero between replays.
 
-What is NOT capturable: stepping an optimizer whose state lives across replays (e.g. a recorded training iteration
-around ``Adam.step()``) -- the recorded bias corrections would be those of the recording step.  That case raises
-(``accelerated_op.adam_op.check_capturable``) instead of replaying wrong numbers.
+Persistent optimizer state: a recorded training iteration around ``Adam.step()`` would replay the bias corrections
+of the recording step, so that raises (``accelerated_op.adam_op.check_capturable``) -- unless the optimizer was built
+with ``capturable=True`` (``Adam`` / ``AdamW`` / ``FlatAdam`` / ``FlatAdamW``): then the step count lives on the device,
+the corrections come from host-computed tables, and every replay is one real, bit-exact optimizer step
+(``b200_adam_step_inplace_capturable``, tests/test_capturable_gpu.py).
 
 Python side effects of ``fn`` (building optimizer objects, re-binding module parameters) run during warm-up and
 capture only; a replay re-executes the recorded GPU work on the static inputs and nothing else.

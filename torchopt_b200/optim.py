@@ -15,6 +15,7 @@ import torch
 from torch import nn
 
 from torchopt_b200 import _pytree
+from torchopt_b200._native import adam_op
 from torchopt_b200.accelerated_op.adam_step import AdamStep
 from torchopt_b200.transform import (GradientTransformation, ScaleByAdamState, inc_count_flat,
                                      scale_by_accelerated_adam)
@@ -197,6 +198,45 @@ def _fused_chain_step(step_op: AdamStep, params: list, grads: list, state: tuple
     return new_params, (*state[:k], ScaleByAdamState(mu=new_mu, nu=new_nu, count=count_inc), *state[k + 1:])
 
 
+class CapturableCounts:
+    """Device-resident step counts + bias-correction tables for an in-place optimizer whose ``step()`` is recorded in a
+    CUDA graph (``capturable=True``).  Nothing about the count is a host scalar any more: ``advance`` increments the
+    counts ON THE DEVICE (one tiny kernel, recorded with the graph) and the step kernel looks the corrections up in
+    tables the host computed once with the reference's own expression -- so results stay bit-identical to the
+    host-scalar path (tests/test_capturable_gpu.py), and every replay advances the optimizer by one real step."""
+
+    def __init__(self, leaves: Sequence[torch.Tensor], b1: float, b2: float) -> None:
+        dev, dtype = leaves[0].device, leaves[0].dtype
+        if any(p.device != dev or p.dtype != dtype for p in leaves):
+            raise ValueError("capturable=True needs all parameters on one device with one dtype")
+        if dev.type != "cuda":
+            raise RuntimeError("Not implemented")     # no CPU path in this package
+        family = 1 if dtype == torch.float64 else 0    # B200_ADAM_F64 / float32 tables (fp32 and bf16 parameters)
+        c1, c2 = adam_op.bias_tables(family, b1, b2)
+        self.c1, self.c2 = c1.to(dev), c2.to(dev)
+        self.vec = torch.zeros(len(leaves), dtype=torch.int64, device=dev)
+        self.counts = list(self.vec.unbind(0))
+
+    def advance(self, live: Sequence[int]) -> None:
+        if len(live) == len(self.counts):
+            self.vec.add_(1)
+        else:
+            for i in live:
+                self.counts[i].add_(1)
+
+
+def _capturable_step(step_op: AdamStep, cap: CapturableCounts, params: list, grads: list, adam_state) -> None:
+    live = [i for i, g in enumerate(grads) if g is not None]
+    if not live:
+        return
+    cap.advance(live)
+    b1, b2, eps, eps_root, step_size, wd_l2, wd_dec, maximize = step_op.hyper
+    adam_op.fused_step_capturable(
+        [params[i].data for i in live], [grads[i] for i in live], [adam_state.mu[i] for i in live],
+        [adam_state.nu[i] for i in live], [cap.counts[i] for i in live], cap.c1, cap.c2, b1, b2, eps, eps_root,
+        step_size, wd_l2, wd_dec, maximize, step_op.keep_grads)
+
+
 class MetaAdam:
     """Differentiable Adam over an ``nn.Module`` (optim/meta/adam.py:33-92 + optim/meta/base.py:35-129).
 
@@ -295,7 +335,9 @@ class Adam:
     # pylint: disable-next=too-many-arguments
     def __init__(self, params: Iterable[torch.Tensor], lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 0.0, *, eps_root: float = 0.0, maximize: bool = False,
-                 use_accelerated_op: bool = True) -> None:
+                 use_accelerated_op: bool = True, capturable: bool = False) -> None:
+        """``capturable=True``: ``step()`` may be recorded in a CUDA graph together with the forward / backward of a
+        training iteration (step counts live on the device, see ``CapturableCounts``); every replay is one real step."""
         self.params = list(params)
         recipe = adamw if self.DECOUPLED else adam
         self.impl = recipe(lr, betas, eps, weight_decay, eps_root=eps_root, maximize=maximize,
@@ -304,6 +346,22 @@ class Adam:
         self.step_op = (AdamStep(betas[0], betas[1], eps, eps_root=eps_root, step_size=-lr, weight_decay=weight_decay,
                                  decoupled=self.DECOUPLED, maximize=maximize, inplace=True) if self.fusable else None)
         self.state = self.impl.init(self.params)
+        self.capturable = None
+        if capturable:
+            if not self.fusable:
+                raise NotImplementedError("capturable=True needs a constant learning rate")
+            self.capturable = CapturableCounts(self.params, betas[0], betas[1])
+            self._bind_capturable_counts()
+
+    def _adam_state_index(self) -> int:
+        return next(i for i, st in enumerate(self.state) if isinstance(st, ScaleByAdamState))
+
+    def _bind_capturable_counts(self) -> None:
+        """The state's ``count`` leaves ARE the device counters (same ScaleByAdamState layout as always)."""
+        k = self._adam_state_index()
+        st = self.state[k]
+        self.state = (*self.state[:k], ScaleByAdamState(mu=st.mu, nu=st.nu, count=self.capturable.counts),
+                      *self.state[k + 1:])
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         for p in self.params:
@@ -316,6 +374,9 @@ class Adam:
     @torch.no_grad()
     def step(self) -> None:
         grads = [p.grad for p in self.params]
+        if self.capturable is not None:
+            _capturable_step(self.step_op, self.capturable, self.params, grads, self.state[self._adam_state_index()])
+            return
         if self.fusable and FUSE_STEP:
             _, self.state = _fused_chain_step(self.step_op, self.params, grads, self.state)
         else:
