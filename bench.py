@@ -475,6 +475,30 @@ def whole_step_kernels(abi, torch, n: int = 1 << 28, iters: int = 20) -> dict:
     total_ms = res["forward"]["ms"] + res["backward"]["ms"]
     res.update(workload=f"whole-step kernels, one flat leaf of {n} fp32 elements (64 B/elem fwd+bwd)",
                gelem_per_s=n / (total_ms * 1e-3) / 1e9)
+    # in-place (non-differentiable) training step on the same arrays: reference side effect (gradients overwritten,
+    # 32 B/elem), gradients left untouched (28 B/elem) and the capturable form (device step count + bias tables)
+    import torchopt_b200 as tb
+    c1, c2 = (x.to(dev) for x in tb.adam_op.bias_tables(0, B1, B2))
+    cnt = torch.full((), COUNT, dtype=torch.int64, device=dev)
+    variants = (
+        ("inplace_overwrite_grads", 32, lambda: abi.step_inplace(abi.F32, P["p"], P["g"], P["mu"], P["nu"], [n], [COUNT],
+                                                                  B1, B2, EPS, EPS_ROOT, -1e-3, s, overwrite_grads=True)),
+        ("inplace_keep_grads", 28, lambda: abi.step_inplace(abi.F32, P["p"], P["g"], P["mu"], P["nu"], [n], [COUNT], B1,
+                                                             B2, EPS, EPS_ROOT, -1e-3, s, overwrite_grads=False)),
+        ("inplace_capturable", 28, lambda: tb.adam_op.fused_step_capturable(
+            [t["p"]], [t["g"]], [t["mu"]], [t["nu"]], [cnt], c1, c2, B1, B2, EPS, EPS_ROOT, -1e-3, 0.0, 0.0, False, True)),
+    )
+    for name, per_elem, fn in variants:
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        res[name] = {"ms": ms, "algorithmic_gbs": per_elem * n / (ms * 1e-3) / 1e9, "gelem_per_s": n / (ms * 1e-3) / 1e9}
     return res
 
 
