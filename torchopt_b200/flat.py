@@ -259,7 +259,8 @@ class FlatAdam:
             return
         _, self.state = _fused_chain_step(self.step_op, [self.flat_p], [self.flat_g], self.state)
 
-    def state_dict(self) -> ScaleByAdamState:
+    def state_dict(self) -> Any:
+        """The chain's state tuple (one entry per transformation; the ``ScaleByAdamState`` holds the flat moments)."""
         return self.state
 
     def load_state_dict(self, state: Any) -> None:
