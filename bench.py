@@ -660,11 +660,23 @@ def run_b200(args) -> None:
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         step_cpu, kind, cores = load_cpu_impl()
         m = min(args.cpu_elems, args.n_total)
-        best = time_cpu(step_cpu, cpu_inputs(m), reps=5, warmup=2)
+        cpu_t = cpu_inputs(m)
+        best = time_cpu(step_cpu, cpu_t, reps=5, warmup=2)
         cpu_baseline = {"value": m / best / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                         "sample": f"{m} of {args.n_total} elements, best of 5 after 2 warm-ups; un-fused forward_mu/nu/"
                                   f"updates + backward_updates/mu/nu + 3 accumulation adds, as autograd runs the "
-                                  f"reference per leaf per step"}
+                                  f"reference per leaf per step",
+                        "host": {"os_cpu_count": os.cpu_count(), "sched_affinity": cores,
+                                 "torch_num_threads": torch.get_num_threads()}}
+        if kind == "reference":   # the reference's only fused CPU kernel: the in-place, non-differentiable forward_
+            from oracle import adam_oracle as ao
+            ref_ops = ao.load_ref().adam_op
+            a, b, c = cpu_t["g"].clone(), cpu_t["mu"].clone(), cpu_t["nu"].clone()
+            best_inplace = time_cpu(lambda _t: ref_ops.forward_(a, b, c, B1, B2, EPS, EPS_ROOT, COUNT), None, reps=5,
+                                    warmup=2)
+            cpu_baseline["forward_inplace"] = {"gelem_per_s": m / best_inplace / 1e9,
+                                               "algorithmic_gbs": 24 * m / best_inplace / 1e9,
+                                               "note": "reference forward_ (in place, 24 B/elem), same sample"}
 
     if world > 1:
         dist.barrier(device_ids=[local_rank])
