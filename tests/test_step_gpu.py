@@ -193,10 +193,12 @@ NO_DECAY = dict(weight_decay=0.0, decoupled=False, maximize=False)
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.bfloat16])
 @pytest.mark.parametrize("recipe", RECIPES + [NO_DECAY])
-def test_adam_step_recipes_equal_torch_chain(dtype, recipe):
+@pytest.mark.parametrize("detached", ["", "g", "g,mu,nu", "p"])
+def test_adam_step_recipes_equal_torch_chain(dtype, recipe, detached):
     """AdamStep (one launch each way) vs the reference's chain evaluated with torch ops on the same GPU:
     g.neg(), g.add(p, alpha=wd), the Adam operator, u.add(p, alpha=wd), u.mul(-lr), p.add(u) -- outputs and all
-    gradients (w.r.t. params, grads, moments) bit-identical."""
+    gradients (w.r.t. params, grads, moments) bit-identical.  ``detached`` names the inputs that do NOT require grad:
+    with first-order (detached) gradients and L2 decay the parameter gradient still needs WD1 * dg2."""
     import torchopt_b200 as tb
     lr, er = 2e-3, 1e-8
     wd, dec, mx = recipe["weight_decay"], recipe["decoupled"], recipe["maximize"]
@@ -220,6 +222,16 @@ def test_adam_step_recipes_equal_torch_chain(dtype, recipe):
     with torch.no_grad():
         for t in g + mu:
             t[::7] = 0
+    off = set(detached.split(",")) - {""}
+    if "p" in off:
+        p = [t.detach() for t in p]
+    if "g" in off:
+        g = [t.detach() for t in g]
+    if "mu" in off:
+        mu = [t.detach() for t in mu]
+    if "nu" in off:
+        nu = [t.detach() for t in nu]
+    wrt = [(name, t) for name, ts in (("dp", p), ("dg", g), ("dmu", mu), ("dnu", nu)) for t in ts if t.requires_grad]
 
     def chain():
         op = tb.AdamOp(eps_root=er, inplace=False)
@@ -242,14 +254,13 @@ def test_adam_step_recipes_equal_torch_chain(dtype, recipe):
     for fn in (chain, fused):
         new_p, new_mu, new_nu = fn()
         total = sum((a * d).sum() for outs, ds in zip((new_p, new_mu, new_nu), douts) for a, d in zip(outs, ds))
-        grads = torch.autograd.grad(total, p + g + mu + nu)
+        grads = torch.autograd.grad(total, [t for _, t in wrt])
         torch.cuda.synchronize()
         res.append(([t.detach() for t in new_p + new_mu + new_nu], grads))
     for a, b in zip(res[0][0], res[1][0]):
         assert torch.equal(a, b), "forward outputs differ from the torch chain"
-    names = ["dp"] * len(sizes) + ["dg"] * len(sizes) + ["dmu"] * len(sizes) + ["dnu"] * len(sizes)
-    for name, a, b in zip(names, res[0][1], res[1][1]):
-        assert torch.equal(a, b), f"{name} differs from the torch chain"
+    for (name, _), a, b in zip(wrt, res[0][1], res[1][1]):
+        assert torch.equal(a, b), f"{name} differs from the torch chain (detached: {detached!r})"
 
 
 @pytest.mark.parametrize("cls_name,wd,mx", [("MetaAdam", 1e-2, False), ("MetaAdam", 1e-2, True), ("MetaAdamW", 1e-2, False),

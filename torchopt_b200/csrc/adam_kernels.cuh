@@ -591,8 +591,13 @@ struct StepBwd {
   static __device__ __forceinline__ bool want_dg(const Leaf &L) { return MODE != BWD_GENERIC || L.dg != nullptr; }
   static __device__ __forceinline__ bool want_dmu(const Leaf &L) { return MODE != BWD_GENERIC || L.dmu != nullptr; }
   static __device__ __forceinline__ bool want_dnu(const Leaf &L) { return MODE != BWD_GENERIC || L.dnu != nullptr; }
+  // dg2 (the gradient w.r.t. the decayed gradient g2) is needed for dg itself AND, with L2 decay, for the parameter
+  // gradient dp_wd = WD1 * dg2 -- also when the caller does not want dg (detached first-order gradients)
+  static __device__ __forceinline__ bool need_dg2(const Leaf &L) {
+    return want_dg(L) || (L.WD1 != CT(0) && want_dp(L));
+  }
   static __device__ __forceinline__ bool need_g(const Leaf &L) {
-    return want_dg(L) && (has_du(L) || has_dnu_ext(L));
+    return need_dg2(L) && (has_du(L) || has_dnu_ext(L));
   }
   template <int P>
   static __device__ __forceinline__ bool aligned(const Leaf &L) {

@@ -519,7 +519,8 @@ static int step_backward_impl(int64_t L, const void *const *dp, const void *cons
     const bool hdp = dp[i] != nullptr, hdus = dus && dus[i] != nullptr;
     const bool hme = dmu_ext[i] != nullptr, hne = dnu_ext[i] != nullptr;
     if ((hdp || hdus) && (!new_mu[i] || !new_nu[i])) return B200_ADAM_E_ARG;
-    if (dg[i] && (hdp || hdus || hne) && !g[i]) return B200_ADAM_E_ARG;
+    const bool want_dg2 = dg[i] || (wd_l2 != 0.0 && dp_out && dp_out[i]);  // dp_wd = wd_l2 * dg2 needs dg2 too
+    if (want_dg2 && (hdp || hdus || hne) && !g[i]) return B200_ADAM_E_ARG;
     if (wd_l2 != 0.0 && g[i] && !(p && p[i])) return B200_ADAM_E_ARG;  // L2 decay: g2 is re-derived from g and p
     const bool outs = dg[i] && dmu[i] && dnu[i];
     all_full = all_full && hdp && !hdus && hme && hne && outs;

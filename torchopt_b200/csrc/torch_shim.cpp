@@ -159,14 +159,51 @@ std::array<Tensor, 2> backward_updates(const Tensor &dupdates_in, const Tensor &
   return {dmu_out, dnu_out};
 }
 
+// ---- leaf layout (multi-tensor entry points only; the seven reference operators keep the reference's raw behaviour) --
+// The kernels walk every array of a leaf linearly (data_ptr()[i], include/utils.h:27-34), so the tensors of ONE leaf
+// must pair element i with element i: non-overlapping, dense, identical strides.  Parameters and their zeros_like
+// moments satisfy that by construction, but gradients handed back by autograd need not (an expanded stride-0 gradient
+// of sum(), a transposed or channels_last view): walking those linearly reads out of bounds or pairs the wrong
+// elements.  `conform` returns `t` itself when it already has the donor's layout and otherwise ONE strided copy of it.
+inline Tensor dense_donor(const Tensor &t) { return t.is_non_overlapping_and_dense() ? t : t.contiguous(); }
+
+inline bool conforms(const Tensor &t, const Tensor &donor) {
+  if (t.sizes() == donor.sizes()) return t.numel() <= 1 || t.strides() == donor.strides();
+  // different shapes with equal numel: flat storage-order pairing like the reference -- fine if both are row-major
+  return t.numel() == donor.numel() && t.is_contiguous() && donor.is_contiguous();
+}
+
+inline Tensor conform(const Tensor &t, const Tensor &donor) {  // `donor` is non-overlapping and dense
+  if (conforms(t, donor)) return t;
+  if (t.sizes() == donor.sizes()) {
+    Tensor out = at::empty_strided(donor.sizes(), donor.strides(), t.options());
+    out.copy_(t);
+    return out;
+  }
+  if (t.numel() != donor.numel())
+    throw std::runtime_error("torchopt_b200: the tensors of one leaf have different numbers of elements");
+  return t.contiguous();
+}
+
+inline void require_inplace_layout(const Tensor &t, const Tensor &donor, const char *what) {
+  if (!donor.is_non_overlapping_and_dense() || !conforms(t, donor))
+    throw std::runtime_error(std::string("torchopt_b200: in-place step: ") + what +
+                             " must be non-overlapping, dense and laid out like the leaf's other tensors");
+}
+
 // ---- flat output allocation -------------------------------------------------------
 // The multi-tensor entry points return up to 4 tensors per leaf.  Allocating them one by one costs ~1.4 us of
 // caching-allocator work each (186 allocations = ~255 us for a ResNet-18-sized pytree, 4x the kernel time).
 // FlatAlloc hands out every output of a call from ONE buffer per (device, dtype): each output has its donor's sizes
 // and (for dense donors) strides -- exactly what empty_like gives -- and starts on a 128-byte boundary.
 // The outputs are independent tensors sharing a storage (Tensor::set_), not autograd views of each other.
+// Only SMALL outputs are pooled (< kPoolMaxBytes each): a pooled output keeps the whole pool alive, which is harmless
+// for the many tiny leaves the pool exists for (41 of ResNet-18's 62 leaves are < 4096 elements) but would let one
+// surviving 64-element tensor pin hundreds of MB if large leaves shared its storage.  Large outputs get their own
+// allocation (the allocator cost is noise next to their kernel time).
 class FlatAlloc {
  public:
+  static constexpr int64_t kPoolMaxBytes = 1 << 20;
   size_t request(const Tensor &donor) {
     reqs_.push_back(&donor);
     return reqs_.size() - 1;
@@ -184,6 +221,10 @@ class FlatAlloc {
     std::map<std::tuple<int, int, int>, Group> groups;
     for (size_t i = 0; i < reqs_.size(); ++i) {
       const Tensor &d = *reqs_[i];
+      if (d.numel() * (int64_t)d.element_size() >= kPoolMaxBytes) {
+        out_[i] = at::empty_like(d);
+        continue;
+      }
       const int64_t align = 128 / (int64_t)d.element_size();
       Group &gr = groups[{(int)d.device().type(), (int)d.device().index(), (int)d.scalar_type()}];
       gr.total = (gr.total + align - 1) / align * align;
@@ -250,27 +291,43 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<OptTensor>> fus
     std::vector<int64_t> n(G);
     std::vector<uint64_t> cnt(G);
     Ctx c(*updates[idx[0]]);
+    // every tensor of a leaf in ONE layout (the first moment's): see `conform`
+    std::vector<Tensor> cg(G), cmu(G), cnu(G);
+    for (size_t k = 0; k < G; ++k) {
+      const size_t i = idx[k];
+      if (inplace) {
+        require_inplace_layout(nu[i], mu[i], "nu");
+        cmu[k] = mu[i], cnu[k] = nu[i];
+      } else {
+        cmu[k] = dense_donor(mu[i]), cnu[k] = conform(nu[i], cmu[k]);
+      }
+      cg[k] = conform(*updates[i], cmu[k]);
+    }
     FlatAlloc fa;
     if (!inplace) {
-      for (size_t k = 0; k < G; ++k) fa.request(mu[idx[k]]), fa.request(nu[idx[k]]), fa.request(*updates[idx[k]]);
+      for (size_t k = 0; k < G; ++k) fa.request(cmu[k]), fa.request(cnu[k]), fa.request(cg[k]);
       fa.commit();
     }
     for (size_t k = 0; k < G; ++k) {
       const size_t i = idx[k];
-      const Tensor &g = *updates[i];
       if (inplace) {
-        new_mu[i] = mu[i], new_nu[i] = nu[i], new_u[i] = g;
+        new_mu[i] = mu[i], new_nu[i] = nu[i], new_u[i] = cg[k];
       } else {
         new_mu[i] = fa[3 * k], new_nu[i] = fa[3 * k + 1], new_u[i] = fa[3 * k + 2];
       }
-      pg[k] = g.data_ptr(), pmu[k] = mu[i].data_ptr(), pnu[k] = nu[i].data_ptr();
+      pg[k] = cg[k].data_ptr(), pmu[k] = cmu[k].data_ptr(), pnu[k] = cnu[k].data_ptr();
       omu[k] = new_mu[i].data_ptr(), onu[k] = new_nu[i].data_ptr(), ou[k] = new_u[i]->data_ptr();
-      n[k] = g.numel(), cnt[k] = count[i];
+      n[k] = cg[k].numel(), cnt[k] = count[i];
     }
     if (inplace) {
       check(b200_adam_forward_inplace_mt(kv.first.dtype, (int64_t)G, ou.data(), omu.data(), onu.data(), n.data(),
                                          cnt.data(), b1, b2, eps, eps_root, c.stream),
             "forward_ (multi-tensor)");
+      for (size_t k = 0; k < G; ++k) {  // a gradient that had to be re-laid-out: write the update back into it
+        const Tensor &g = *updates[idx[k]];
+        if (!cg[k].is_same(g)) const_cast<Tensor &>(g).copy_(cg[k]);
+        new_u[idx[k]] = g;
+      }
     } else {
       check(b200_adam_fused_forward(kv.first.dtype, (int64_t)G, pg.data(), pmu.data(), pnu.data(), omu.data(),
                                     onu.data(), ou.data(), n.data(), cnt.data(), b1, b2, eps, eps_root, c.stream),
@@ -295,7 +352,9 @@ std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor
   std::vector<OptTensor> dg(L), dmu(L), dnu(L);
   std::vector<long> slot_dg(L, -1), slot_dmu(L, -1), slot_dnu(L, -1);
   FlatAlloc fa;
-  std::vector<Tensor> cdu(L), cme(L), cne(L);  // keep the .contiguous() copies alive until after the launch
+  // every array of a leaf in the layout of its saved new_mu (`conform`: incoming gradients may be expanded / permuted
+  // views; the reference only makes them row-major, adam_op.cpp:107,123,144, which mis-pairs a channels_last leaf)
+  std::vector<Tensor> cdu(L), cme(L), cne(L), cu(L), cm(L), cg(L);  // kept alive until after the launch
   std::map<GroupKey, std::vector<size_t>> groups;
   for (size_t i = 0; i < L; ++i) {
     const bool hdu = dupdates[i].has_value(), hme = dmu_ext[i].has_value(), hne = dnu_ext[i].has_value();
@@ -304,12 +363,13 @@ std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor
     if (!wg && !wm && !wn) continue;
     require_cuda(g[i]);
     const int dt = family(g[i], new_mu[i], "adamBackwardUpdatesCUDA", true);
-    if (hdu) cdu[i] = dupdates[i]->contiguous(), same_type(cdu[i], g[i]);
-    if (hme) cme[i] = dmu_ext[i]->contiguous(), same_type(cme[i], new_mu[i]);
-    if (hne) cne[i] = dnu_ext[i]->contiguous(), same_type(cne[i], new_mu[i]);
-    if (wg) slot_dg[i] = (long)fa.request(g[i]);
-    if (wm) slot_dmu[i] = (long)fa.request(new_mu[i]);
-    if (wn) slot_dnu[i] = (long)fa.request(new_mu[i]);
+    cm[i] = dense_donor(new_mu[i]), cu[i] = conform(new_updates[i], cm[i]), cg[i] = conform(g[i], cm[i]);
+    if (hdu) cdu[i] = conform(*dupdates[i], cm[i]), same_type(cdu[i], g[i]);
+    if (hme) cme[i] = conform(*dmu_ext[i], cm[i]), same_type(cme[i], new_mu[i]);
+    if (hne) cne[i] = conform(*dnu_ext[i], cm[i]), same_type(cne[i], new_mu[i]);
+    if (wg) slot_dg[i] = (long)fa.request(cg[i]);
+    if (wm) slot_dmu[i] = (long)fa.request(cm[i]);
+    if (wn) slot_dnu[i] = (long)fa.request(cm[i]);
     groups[GroupKey{(int)g[i].device().index(), dt}].push_back(i);
   }
   fa.commit();
@@ -331,11 +391,11 @@ std::tuple<std::vector<OptTensor>, std::vector<OptTensor>, std::vector<OptTensor
       pdu[k] = cdu[i].defined() ? cdu[i].data_ptr() : nullptr;
       pme[k] = cme[i].defined() ? cme[i].data_ptr() : nullptr;
       pne[k] = cne[i].defined() ? cne[i].data_ptr() : nullptr;
-      pu[k] = new_updates[i].data_ptr(), pm[k] = new_mu[i].data_ptr(), pg[k] = g[i].data_ptr();
+      pu[k] = cu[i].data_ptr(), pm[k] = cm[i].data_ptr(), pg[k] = cg[i].data_ptr();
       odg[k] = dg[i] ? dg[i]->data_ptr() : nullptr;
       odm[k] = dmu[i] ? dmu[i]->data_ptr() : nullptr;
       odn[k] = dnu[i] ? dnu[i]->data_ptr() : nullptr;
-      n[k] = g[i].numel(), cnt[k] = count[i];
+      n[k] = cg[i].numel(), cnt[k] = count[i];
     }
     check(b200_adam_fused_backward(kv.first.dtype, (int64_t)G, pdu.data(), pu.data(), pm.data(), pg.data(), pme.data(),
                                    pne.data(), odg.data(), odm.data(), odn.data(), n.data(), cnt.data(), b1, b2,
@@ -377,29 +437,40 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>, std::v
     std::vector<int64_t> n(G);
     std::vector<uint64_t> cnt(G);
     Ctx c(params[idx[0]]);
+    // every tensor of a leaf in ONE layout (the parameter's): see `conform`
+    std::vector<Tensor> cp(G), cg(G), cmu(G), cnu(G);
+    for (size_t k = 0; k < G; ++k) {
+      const size_t i = idx[k];
+      if (inplace) {
+        require_inplace_layout(mu[i], params[i], "mu"), require_inplace_layout(nu[i], params[i], "nu");
+        cp[k] = params[i], cmu[k] = mu[i], cnu[k] = nu[i];
+      } else {
+        cp[k] = dense_donor(params[i]), cmu[k] = conform(mu[i], cp[k]), cnu[k] = conform(nu[i], cp[k]);
+      }
+      cg[k] = conform(*grads[i], cp[k]);
+    }
     FlatAlloc fa;
     const size_t per_leaf = want_updates ? 4 : 3;
     if (!inplace) {
       for (size_t k = 0; k < G; ++k) {
-        fa.request(params[idx[k]]), fa.request(mu[idx[k]]), fa.request(nu[idx[k]]);
-        if (want_updates) fa.request(*grads[idx[k]]);
+        fa.request(cp[k]), fa.request(cmu[k]), fa.request(cnu[k]);
+        if (want_updates) fa.request(cg[k]);
       }
       fa.commit();
     }
     for (size_t k = 0; k < G; ++k) {
       const size_t i = idx[k];
-      const Tensor &g = *grads[i];
       if (inplace) {
         new_p[i] = params[i], new_mu[i] = mu[i], new_nu[i] = nu[i];
-        if (!keep_grads) new_us[i] = g;   // reference side effect: the gradient tensor becomes the scaled update
+        if (!keep_grads) new_us[i] = cg[k];   // reference side effect: the gradient tensor becomes the scaled update
       } else {
         new_p[i] = fa[per_leaf * k], new_mu[i] = fa[per_leaf * k + 1], new_nu[i] = fa[per_leaf * k + 2];
         if (want_updates) new_us[i] = fa[per_leaf * k + 3];
       }
-      pp[k] = params[i].data_ptr(), pg[k] = g.data_ptr(), pmu[k] = mu[i].data_ptr(), pnu[k] = nu[i].data_ptr();
+      pp[k] = cp[k].data_ptr(), pg[k] = cg[k].data_ptr(), pmu[k] = cmu[k].data_ptr(), pnu[k] = cnu[k].data_ptr();
       op[k] = new_p[i].data_ptr(), omu[k] = new_mu[i].data_ptr(), onu[k] = new_nu[i].data_ptr();
       ous[k] = new_us[i] ? new_us[i]->data_ptr() : nullptr;
-      n[k] = g.numel(), cnt[k] = count[i];
+      n[k] = cg[k].numel(), cnt[k] = count[i];
     }
     if (inplace) {
       std::vector<void *> gio(G);
@@ -408,6 +479,12 @@ std::tuple<std::vector<Tensor>, std::vector<Tensor>, std::vector<Tensor>, std::v
                                       cnt.data(), b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled,
                                       maximize ? 1 : 0, keep_grads ? 0 : 1, c.stream),
             "fused_step (inplace)");
+      if (!keep_grads)
+        for (size_t k = 0; k < G; ++k) {  // a gradient that had to be re-laid-out: write the update back into it
+          const Tensor &g = *grads[idx[k]];
+          if (!cg[k].is_same(g)) const_cast<Tensor &>(g).copy_(cg[k]);
+          new_us[idx[k]] = g;
+        }
     } else {
       check(b200_adam_step_forward(kv.first.dtype, (int64_t)G, pp.data(), pg.data(), pmu.data(), pnu.data(), op.data(),
                                    omu.data(), onu.data(), ous.data(), n.data(), cnt.data(), b1, b2, eps, eps_root,
@@ -438,7 +515,7 @@ fused_step_backward(
   std::vector<OptTensor> dg(L), dmu(L), dnu(L), dp(L);
   std::vector<long> slot_dg(L, -1), slot_dmu(L, -1), slot_dnu(L, -1), slot_dp(L, -1);
   FlatAlloc fa;
-  std::vector<Tensor> cdp(L), cdus(L), cme(L), cne(L);
+  std::vector<Tensor> cdp(L), cdus(L), cme(L), cne(L), cm(L), cv(L), cg(L), cpar(L);  // see `conform`
   std::map<GroupKey, std::vector<size_t>> groups;
   for (size_t i = 0; i < L; ++i) {
     const bool hdu = dparams[i].has_value() || dus[i].has_value();
@@ -452,14 +529,16 @@ fused_step_backward(
     const int dt = family(g[i], new_mu[i], "adamStepBackwardCUDA", true);
     if (wd_l2 != 0.0 && !params[i].has_value())
       throw std::runtime_error("fused_step_backward: params are required for L2 weight decay");
-    if (wp) slot_dp[i] = (long)fa.request(g[i]);
-    if (dparams[i]) cdp[i] = dparams[i]->contiguous(), same_type(cdp[i], g[i]);
-    if (dus[i]) cdus[i] = dus[i]->contiguous(), same_type(cdus[i], g[i]);
-    if (hme) cme[i] = dmu_ext[i]->contiguous(), same_type(cme[i], new_mu[i]);
-    if (hne) cne[i] = dnu_ext[i]->contiguous(), same_type(cne[i], new_mu[i]);
-    if (wg) slot_dg[i] = (long)fa.request(g[i]);
-    if (wm) slot_dmu[i] = (long)fa.request(new_mu[i]);
-    if (wn) slot_dnu[i] = (long)fa.request(new_nu[i]);
+    cm[i] = dense_donor(new_mu[i]), cv[i] = conform(new_nu[i], cm[i]), cg[i] = conform(g[i], cm[i]);
+    if (params[i]) cpar[i] = conform(*params[i], cm[i]);
+    if (wp) slot_dp[i] = (long)fa.request(cg[i]);
+    if (dparams[i]) cdp[i] = conform(*dparams[i], cm[i]), same_type(cdp[i], g[i]);
+    if (dus[i]) cdus[i] = conform(*dus[i], cm[i]), same_type(cdus[i], g[i]);
+    if (hme) cme[i] = conform(*dmu_ext[i], cm[i]), same_type(cme[i], new_mu[i]);
+    if (hne) cne[i] = conform(*dnu_ext[i], cm[i]), same_type(cne[i], new_mu[i]);
+    if (wg) slot_dg[i] = (long)fa.request(cg[i]);
+    if (wm) slot_dmu[i] = (long)fa.request(cm[i]);
+    if (wn) slot_dnu[i] = (long)fa.request(cv[i]);
     groups[GroupKey{(int)g[i].device().index(), dt}].push_back(i);
   }
   fa.commit();
@@ -483,13 +562,13 @@ fused_step_backward(
       pdus[k] = cdus[i].defined() ? cdus[i].data_ptr() : nullptr;
       pme[k] = cme[i].defined() ? cme[i].data_ptr() : nullptr;
       pne[k] = cne[i].defined() ? cne[i].data_ptr() : nullptr;
-      pm[k] = new_mu[i].data_ptr(), pv[k] = new_nu[i].data_ptr(), pg[k] = g[i].data_ptr();
+      pm[k] = cm[i].data_ptr(), pv[k] = cv[i].data_ptr(), pg[k] = cg[i].data_ptr();
       odg[k] = dg[i] ? dg[i]->data_ptr() : nullptr;
       odm[k] = dmu[i] ? dmu[i]->data_ptr() : nullptr;
       odn[k] = dnu[i] ? dnu[i]->data_ptr() : nullptr;
-      pp[k] = params[i] ? params[i]->data_ptr() : nullptr;
+      pp[k] = cpar[i].defined() ? cpar[i].data_ptr() : nullptr;
       odp[k] = (decay && dp[i]) ? dp[i]->data_ptr() : nullptr;
-      n[k] = g[i].numel(), cnt[k] = count[i];
+      n[k] = cg[i].numel(), cnt[k] = count[i];
     }
     check(b200_adam_step_backward(kv.first.dtype, (int64_t)G, pdp.data(), pdus.data(), pm.data(), pv.data(), pg.data(),
                                   pme.data(), pne.data(), odg.data(), odm.data(), odn.data(), pp.data(), odp.data(),
@@ -540,6 +619,9 @@ void fused_step_capturable(const std::vector<Tensor> &params, const std::vector<
     same_type(mu[i], nu[i]), same_type(grads[i], params[i]);
     if (!count[i].is_cuda() || count[i].scalar_type() != at::kLong || count[i].numel() != 1)
       throw std::runtime_error("fused_step_capturable: step counts must be one-element int64 CUDA tensors");
+    // a recorded step cannot hide a re-layout copy: every tensor of the leaf must already share the parameter's layout
+    require_inplace_layout(grads[i], params[i], "the gradient");
+    require_inplace_layout(mu[i], params[i], "mu"), require_inplace_layout(nu[i], params[i], "nu");
     pp[i] = params[i].data_ptr(), pg[i] = grads[i].data_ptr(), pmu[i] = mu[i].data_ptr(), pnu[i] = nu[i].data_ptr();
     pc[i] = count[i].data_ptr<int64_t>(), n[i] = grads[i].numel();
   }
