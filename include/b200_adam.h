@@ -226,6 +226,13 @@ uint64_t b200_adam_kernel_launches(void);
  * Process-wide; intended for the bench/tuning harness. */
 int b200_adam_set_tuning(int ctas_per_sm, int tiles_per_chunk);
 
+/* Programmatic dependent launch (default on): every kernel is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, waits (griddepcontrol.wait) for the work before it in the stream
+ * before its first global access and lets the next kernel's CTAs become resident while its own last wave drains -- the
+ * launch gap between the back-to-back kernels of an unroll (~3 us each) is hidden.  enabled = 0 restores plain stream
+ * serialisation.  Process-wide; results are identical either way. */
+int b200_adam_set_pdl(int enabled);
+
 /* Writes the launch geometry the library would use for an `n`-element single-leaf fused launch:
  * out[0]=grid, out[1]=block, out[2]=elements per chunk, out[3]=vector width in elements, out[4]=unroll. */
 int b200_adam_query_launch(int dtype, int backward, int64_t n, int32_t out[5]);

@@ -45,36 +45,81 @@ def load_ref_cuda():
     return mod.adam_op
 
 
-def time_ms(torch, fn, iters=20, warmup=5):
+def time_ms(torch, fn, iters=20, warmup=5, repeats=1):
+    """best of ``repeats`` timings of ``iters`` calls (CUDA events on the current stream)"""
     for _ in range(warmup):
         fn()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        fn()
-    e1.record()
+    best = float("inf")
+    for _ in range(repeats):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / iters)
+    return best
+
+
+def spin_up(torch, seconds=0.5):
+    """Bring the GPU out of its idle power state before the first (smallest, launch-bound) measurement: round 1's
+    sweep started cold and its first row (2^12: 30 us) was slower than its third (2^16: 11 us) for that reason only."""
+    import time
+    a = torch.empty(1 << 26, device="cuda")
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(20):
+            a.add_(1.0)
+        torch.cuda.synchronize()
+    del a
+
+
+def graph_ms(torch, step, steps_per_graph=20, replays=10):
+    """ms per step with ``steps_per_graph`` steps recorded in ONE CUDA graph: no host launch cost at all, i.e. what the
+    device itself needs for the back-to-back launches (programmatic edges between them when PDL is on)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step(side.cuda_stream)
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        for _ in range(steps_per_graph):
+            step(torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        g.replay()
+    best = float("inf")
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(replays):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / (replays * steps_per_graph))
+    return best
 
 
-def make_leaves(torch, sizes, grad_dtype):
+def make_leaves(torch, sizes, grad_dtype, state_dtype=None):
     dev = torch.device("cuda")
+    sd = state_dtype or torch.float32
     t = {k: [] for k in ("g", "mu", "nu", "du", "dme", "dne", "mu2", "nu2", "u", "dg", "dmu", "dnu")}
     for n in sizes:
         t["g"].append((torch.randn(n, device=dev) * 1e-2).to(grad_dtype))
-        t["mu"].append(torch.randn(n, device=dev) * 1e-2)
-        t["nu"].append(torch.rand(n, device=dev) * 1e-4)
+        t["mu"].append((torch.randn(n, device=dev) * 1e-2).to(sd))
+        t["nu"].append((torch.rand(n, device=dev) * 1e-4).to(sd))
         t["du"].append(torch.randn(n, device=dev).to(grad_dtype))
-        t["dme"].append(torch.randn(n, device=dev) * 1e-3)
-        t["dne"].append(torch.randn(n, device=dev) * 1e-3)
+        t["dme"].append((torch.randn(n, device=dev) * 1e-3).to(sd))
+        t["dne"].append((torch.randn(n, device=dev) * 1e-3).to(sd))
         for k in ("mu2", "nu2", "dmu", "dnu"):
-            t[k].append(torch.empty(n, device=dev))
+            t[k].append(torch.empty(n, device=dev, dtype=sd))
         for k in ("u", "dg"):
             t[k].append(torch.empty(n, device=dev, dtype=grad_dtype))
     return t
 
 
-def ours(torch, abi, t, sizes, dtype, per_leaf=False):
+def ours(torch, abi, t, sizes, dtype, per_leaf=False, graph=False, iters=20, repeats=1):
     ptr = {k: [x.data_ptr() for x in v] for k, v in t.items()}
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -86,13 +131,15 @@ def ours(torch, abi, t, sizes, dtype, per_leaf=False):
 
     preps = [prep([i]) for i in range(len(sizes))] if per_leaf else [prep(list(range(len(sizes))))]
 
-    def step():
+    def step(s=stream):
         for p in preps:
-            p.forward(stream)
+            p.forward(s)
         for p in preps:
-            p.backward(stream)
+            p.backward(s)
 
-    return time_ms(torch, step)
+    if graph:
+        return graph_ms(torch, step)
+    return time_ms(torch, step, iters=iters, repeats=repeats)
 
 
 def reference(torch, ref, t, sizes):
@@ -127,14 +174,29 @@ def main():
     ref = load_ref_cuda()
     torch.manual_seed(0)
     rows = []
+    spin_up(torch)
     for lg in range(12, args.max_log2 + 1, 2):
         n = 1 << lg
-        for name, gd, dt, bpe in (("fp32", torch.float32, abi.F32, 60), ("bf16-grad/fp32-state", torch.bfloat16, abi.BF16_F32, 50)):
-            t = make_leaves(torch, [n], gd)
-            ms = ours(torch, abi, t, [n], dt)
+        for name, gd, sd, dt, bpe in (("fp32", torch.float32, torch.float32, abi.F32, 60),
+                                      ("bf16-grad/fp32-state", torch.bfloat16, torch.float32, abi.BF16_F32, 50),
+                                      ("fp64", torch.float64, torch.float64, abi.F64, 120)):
+            if name == "fp64" and lg > 28:
+                continue    # 12 fp64 arrays of 2^30 elements do not fit next to the allocator's cache
+            t = make_leaves(torch, [n], gd, sd)
+            small = lg <= 22
+            ms = ours(torch, abi, t, [n], dt, iters=200 if small else 20, repeats=3)
             row = {"case": "single leaf", "n": n, "log2n": lg, "dtype": name, "ours_ms": ms,
                    "ours_gelem_s": n / (ms * 1e-3) / 1e9, "ours_gbs": bpe * n / (ms * 1e-3) / 1e9,
-                   "fits_l2": 12 * 4 * n < 100e6}
+                   "fits_l2": 12 * t["g"][0].element_size() * n < 100e6}
+            if lg <= 26:
+                # the same two launches per step recorded in a CUDA graph (no host launch cost), with and without PDL
+                gms = ours(torch, abi, t, [n], dt, graph=True)
+                abi.set_pdl(False)
+                gms_plain = ours(torch, abi, t, [n], dt, graph=True)
+                ms_plain = ours(torch, abi, t, [n], dt, iters=200 if small else 20, repeats=3)
+                abi.set_pdl(True)
+                row.update(ours_graph_ms=gms, ours_graph_gbs=bpe * n / (gms * 1e-3) / 1e9, ours_graph_no_pdl_ms=gms_plain,
+                           ours_no_pdl_ms=ms_plain)
             if gd == torch.float32:
                 # the same nine calls per leaf through THIS repo's drop-in `_C.adam_op` surface (no Python changes
                 # on the TorchOpt side: INTEGRATION.md section 2 only)

@@ -1,6 +1,7 @@
-"""The native autograd nodes (torch_shim.cpp: FusedNode, StepNode) against the Python autograd.Functions they replace
-(AdamOp.FusedOp, AdamStep.Op): same values, same gradients, same None patterns, bit for bit -- they call the same
-kernels with the same arguments; only the bookkeeping moves from the interpreter to C++."""
+"""The native autograd nodes (torch_shim.cpp: FusedNode, StepNode, and FlatStepNode -- the default path of the optimizer
+classes, flat moment buffers) against the Python autograd.Functions they replace (AdamOp.FusedOp, AdamStep.Op, per-leaf
+state): same values, same gradients, same None patterns, bit for bit -- they call the same kernels with the same
+arguments; only the bookkeeping moves from the interpreter to C++ and from 4L tensors to 2L+2."""
 from __future__ import annotations
 
 import contextlib
@@ -15,12 +16,15 @@ SIZES = [5, 64, 321, 4097, 36_864]
 
 @contextlib.contextmanager
 def python_nodes():
+    from torchopt_b200 import optim
     from torchopt_b200.accelerated_op import adam_op, adam_step
     adam_op.NATIVE_NODE = adam_step.NATIVE_NODE = False
+    optim.FLAT_STATE = False    # per-leaf state: the optimizers go through AdamStep.Op instead of the flat-state node
     try:
         yield
     finally:
         adam_op.NATIVE_NODE = adam_step.NATIVE_NODE = True
+        optim.FLAT_STATE = True
 
 
 def same(a, b):

@@ -55,3 +55,29 @@ def fwd_only():
     return cur
 timeit("5-step unroll forward only", fwd_only, iters=20)
 timeit("opt.impl.init (62 leaves zeros + counts)", lambda: opt.impl.init(pd), iters=50)
+
+
+# ---- round 2: the default state layout (flat moment buffers, host counts) vs the per-leaf reference layout ----------
+from torchopt_b200 import optim  # noqa: E402
+gd = [x.detach() for x in g]
+
+
+def five_steps(flat):
+    optim.FLAT_STATE = flat
+    o = tb.FuncAdam(1e-3)
+    cur = list(p)
+    for _ in range(5):
+        cur = o.apply_gradients(gd, cur)
+    return cur
+
+
+def five_steps_and_backward(flat):
+    cur = five_steps(flat)
+    return torch.autograd.grad(torch.stack([q.sum() for q in cur]).sum(), p)
+
+
+for flat in (True, False):
+    tag = "flat moment buffers (default)" if flat else "per-leaf state (optim.FLAT_STATE = False)"
+    timeit(f"5 x FuncAdam.apply_gradients, {tag}", lambda: five_steps(flat), iters=40)
+    timeit(f"  + meta-backward (62 sums + stack), {tag}", lambda: five_steps_and_backward(flat), iters=40)
+optim.FLAT_STATE = True

@@ -60,6 +60,7 @@ SYMBOLS = {
     "b200_adam_error_string": (c_char_p, [c_int]),
     "b200_adam_kernel_launches": (c_uint64, []),
     "b200_adam_set_tuning": (c_int, [c_int, c_int]),
+    "b200_adam_set_pdl": (c_int, [c_int]),
     "b200_adam_query_launch": (c_int, [c_int, c_int, c_int64, POINTER(c_int32)]),
 }
 
@@ -93,8 +94,20 @@ def check(rc: int, what: str = "b200_adam") -> None:
         raise B200AdamError(f"{what}: {load().b200_adam_error_string(rc).decode()} (code {rc})")
 
 
+_ARR_CACHE: dict = {}
+_ARR_CACHE_MAX = 512
+
+
 def _arr(ctype, values):
-    return (ctype * len(values))(*values)
+    """ctypes array of ``values``; cached by content (the same leaf set is marshalled once, not once per call -- the
+    arrays are only read by the library)."""
+    key = (ctype, tuple(values))
+    hit = _ARR_CACHE.get(key)
+    if hit is None:
+        if len(_ARR_CACHE) >= _ARR_CACHE_MAX:
+            _ARR_CACHE.clear()
+        hit = _ARR_CACHE[key] = (ctype * len(key[1]))(*key[1])
+    return hit
 
 
 def _ptrs(ptrs):
@@ -224,6 +237,10 @@ def kernel_launches() -> int:
 
 def set_tuning(ctas_per_sm: int = 0, tiles_per_chunk: int = 0) -> None:
     check(load().b200_adam_set_tuning(ctas_per_sm, tiles_per_chunk), "set_tuning")
+
+
+def set_pdl(enabled: bool = True) -> None:
+    check(load().b200_adam_set_pdl(int(bool(enabled))), "set_pdl")
 
 
 def query_launch(dtype: int, backward: bool, n: int) -> dict:

@@ -803,8 +803,21 @@ __device__ __forceinline__ void process_chunk(const typename Op::Leaf &L, long l
   }
 }
 
+// Programmatic dependent launch (PDL): every launch carries cudaLaunchAttributeProgrammaticStreamSerialization
+// (b200_adam.cu:launch_table).  `griddepcontrol.wait` blocks until the grids this one depends on have completed and
+// flushed -- it precedes every global access, so correctness does not depend on what the previous kernel was --
+// and `griddepcontrol.launch_dependents` lets the NEXT grid's CTAs become resident as soon as all of this grid's CTAs
+// have started, i.e. while the last wave drains: the ~3 us launch gap between the back-to-back kernels of an unroll
+// disappears (profiles/r01_pdl_experiment.md: +4 % at 2^24 elements; r02_leaf_sweep.md).  Both are no-ops for a grid
+// launched without the attribute.
+__device__ __forceinline__ void pdl_wait_then_release() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 template <class Op, int P, int U, int BLOCK, int MAXL>
 __global__ void __launch_bounds__(BLOCK) stream_kernel(const __grid_constant__ Table<Op, MAXL> tab) {
+  pdl_wait_then_release();
   for (int c = blockIdx.x; c < tab.total_chunks; c += gridDim.x) {
     int l = 0;
     if constexpr (MAXL > 1) {

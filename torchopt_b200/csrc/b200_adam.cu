@@ -57,6 +57,7 @@ struct Cfg<bf16_t, float> {
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_ctas_per_sm{0};
 static std::atomic<int> g_tiles_per_chunk{0};
+static std::atomic<int> g_pdl{1};  // programmatic dependent launch on every launch (b200_adam_set_pdl)
 
 struct DeviceInfo {
   int sms = 0;
@@ -122,9 +123,15 @@ static int launch_table(Table<Op, MAXL> &tab, const DeviceInfo &di, cudaStream_t
   const int per_sm = g_ctas_per_sm.load(std::memory_order_relaxed);
   long long grid = tab.total_chunks;
   if (per_sm > 0 && (long long)di.sms * per_sm < grid) grid = (long long)di.sms * per_sm;
-  stream_kernel<Op, P, U, BLOCK, MAXL><<<(unsigned)grid, BLOCK, 0, stream>>>(tab);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(BLOCK), cfg.dynamicSmemBytes = 0, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, stream_kernel<Op, P, U, BLOCK, MAXL>, tab);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  return (int)cudaGetLastError();
+  return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 // Feeds leaves (produced by `next(i, leaf)`, which returns false for a leaf to skip) through tables of
@@ -610,6 +617,11 @@ int b200_adam_set_tuning(int ctas_per_sm, int tiles_per_chunk) {
   if (ctas_per_sm < 0 || tiles_per_chunk < 0) return B200_ADAM_E_ARG;
   g_ctas_per_sm.store(ctas_per_sm);
   g_tiles_per_chunk.store(tiles_per_chunk);
+  return 0;
+}
+
+int b200_adam_set_pdl(int enabled) {
+  g_pdl.store(enabled ? 1 : 0);
   return 0;
 }
 

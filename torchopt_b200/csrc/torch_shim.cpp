@@ -761,6 +761,254 @@ struct StepNode : public torch::autograd::Function<StepNode> {
   }
 };
 
+// ---- flat-state whole step (the default path of MetaAdam / FuncAdam / Adam) -------------------------------------------
+// The per-leaf nodes above hand autograd 4L inputs and 3L outputs per step; most of the host time of a 62-leaf step
+// is that bookkeeping.  Here the moments of ALL leaves of one (device, dtype) group live in ONE buffer each
+// (mu_flat, nu_flat; live leaf k occupies [offs[k], offs[k] + numel_k), 128-byte aligned), so autograd sees
+// 2K + 2 inputs and K + 2 outputs; the parameters and gradients stay per-leaf tensors (the caller's model needs them that
+// way) and reach the kernel through the leaf table like before.  Leaves WITHOUT a gradient this step are not passed at
+// all: their parameters are not touched and their moment ranges (`keep` = begin/end pairs) are copied through, which is
+// the reference's skip semantics (accelerated_op/adam_op.py:148-149, optim/meta/base.py:58-96).
+// Padding between leaves is never read by any kernel and holds unspecified values.
+inline int flat_family(const Tensor &p, const Tensor &mu_flat) { return family(p, mu_flat, "adamStepCUDA", true); }
+
+struct FlatPtrs {
+  std::vector<const void *> p, g, mu, nu, dp, dme, dne;
+  std::vector<void *> po, muo, nuo, dg, dmu, dnu, dpo;
+  std::vector<int64_t> n;
+  std::vector<uint64_t> cnt;
+  explicit FlatPtrs(size_t K)
+      : p(K), g(K), mu(K), nu(K), dp(K), dme(K), dne(K), po(K), muo(K), nuo(K), dg(K), dmu(K), dnu(K), dpo(K), n(K),
+        cnt(K) {}
+};
+
+inline char *at_offset(const Tensor &flat, int64_t off) {
+  return flat.defined() ? (char *)flat.data_ptr() + off * (int64_t)flat.element_size() : nullptr;
+}
+
+inline void copy_ranges(Tensor &dst, const Tensor &src, const std::vector<int64_t> &keep) {
+  for (size_t r = 0; r + 1 < keep.size(); r += 2)
+    if (keep[r + 1] > keep[r]) dst.narrow(0, keep[r], keep[r + 1] - keep[r]).copy_(src.narrow(0, keep[r], keep[r + 1] - keep[r]));
+}
+
+// forward without autograd: returns p'_0.., mu'_flat, nu'_flat ; `cp`, `cg` receive the row-major tensors actually read
+variable_list flat_step_forward(at::TensorList tensors, const std::vector<int64_t> &offs, const std::vector<int64_t> &keep,
+                                const std::vector<int64_t> &counts, const std::vector<double> &hyper,
+                                std::vector<Tensor> &cp, std::vector<Tensor> &cg) {
+  const size_t K = counts.size();
+  if (tensors.size() != 2 * K + 2 || offs.size() != K || hyper.size() != 8)
+    throw std::runtime_error("flat_step: expected p_0.., g_0.., mu_flat, nu_flat with one offset and count per leaf");
+  const Tensor &mu_flat = tensors[2 * K], &nu_flat = tensors[2 * K + 1];
+  if (mu_flat.dim() != 1 || !mu_flat.is_contiguous() || !nu_flat.is_contiguous() || mu_flat.sizes() != nu_flat.sizes())
+    throw std::runtime_error("flat_step: the flat moment buffers must be contiguous 1-D tensors of equal length");
+  require_cuda(mu_flat);
+  same_type(mu_flat, nu_flat);
+  Tensor mu_out = at::empty_like(mu_flat), nu_out = at::empty_like(nu_flat);
+  copy_ranges(mu_out, mu_flat, keep), copy_ranges(nu_out, nu_flat, keep);
+  variable_list result;
+  result.reserve(K + 2);
+  if (K > 0) {
+    const int dt = flat_family(tensors[0], mu_flat);
+    Ctx c(mu_flat);
+    FlatAlloc fa;
+    cp.resize(K), cg.resize(K);
+    for (size_t k = 0; k < K; ++k) {
+      const Tensor &p = tensors[k], &g = tensors[K + k];
+      if (flat_family(p, mu_flat) != dt || p.device() != mu_flat.device())
+        throw std::runtime_error("flat_step: all leaves of a group must share one device and one dtype family");
+      same_type(p, g);
+      cp[k] = p.is_contiguous() ? p : p.contiguous();  // flat moments are row-major: so is every array of the leaf
+      cg[k] = conform(g, cp[k]);
+      if (offs[k] < 0 || offs[k] + cp[k].numel() > mu_flat.numel())
+        throw std::runtime_error("flat_step: a leaf does not fit the flat moment buffers");
+      fa.request(cp[k]);
+    }
+    fa.commit();
+    FlatPtrs q(K);
+    for (size_t k = 0; k < K; ++k) {
+      result.push_back(fa[k]);
+      q.p[k] = cp[k].data_ptr(), q.g[k] = cg[k].data_ptr();
+      q.mu[k] = at_offset(mu_flat, offs[k]), q.nu[k] = at_offset(nu_flat, offs[k]);
+      q.po[k] = fa[k].data_ptr(), q.muo[k] = at_offset(mu_out, offs[k]), q.nuo[k] = at_offset(nu_out, offs[k]);
+      q.n[k] = cp[k].numel(), q.cnt[k] = (uint64_t)counts[k];
+    }
+    check(b200_adam_step_forward(dt, (int64_t)K, q.p.data(), q.g.data(), q.mu.data(), q.nu.data(), q.po.data(),
+                                 q.muo.data(), q.nuo.data(), nullptr, q.n.data(), q.cnt.data(), hyper[0], hyper[1],
+                                 hyper[2], hyper[3], hyper[4], hyper[5], hyper[6], hyper[7] != 0.0 ? 1 : 0, c.stream),
+          "flat_step");
+  }
+  result.push_back(mu_out), result.push_back(nu_out);
+  return result;
+}
+
+struct FlatStepNode : public torch::autograd::Function<FlatStepNode> {
+  static variable_list forward(AutogradContext *ctx, at::TensorList tensors, std::vector<int64_t> offs,
+                               std::vector<int64_t> keep, std::vector<int64_t> counts, std::vector<double> hyper) {
+    const size_t K = counts.size();
+    std::vector<Tensor> cp, cg;
+    variable_list result = flat_step_forward(tensors, offs, keep, counts, hyper, cp, cg);
+    ctx->set_materialize_grads(false);
+    ctx->saved_data["offs"] = offs, ctx->saved_data["keep"] = keep;
+    ctx->saved_data["counts"] = counts, ctx->saved_data["hyper"] = hyper;
+    variable_list saved;
+    saved.reserve(2 * K + 2);
+    saved.push_back(result[K]), saved.push_back(result[K + 1]);  // mu', nu' (u is recomputed in the backward kernel)
+    // the tensor the kernel read is saved: the caller's own gradient when it was already row-major (then it is an INPUT,
+    // saved without a reference cycle), a private copy otherwise
+    for (size_t k = 0; k < K; ++k) saved.push_back(cg[k]);
+    if (hyper[5] != 0.0)
+      for (size_t k = 0; k < K; ++k) saved.push_back(cp[k]);  // L2 decay: g2 = g + wd * p is re-derived
+    ctx->save_for_backward(saved);
+    return result;
+  }
+
+  static variable_list backward(AutogradContext *ctx, variable_list douts) {
+    const auto offs = ctx->saved_data["offs"].toIntVector();
+    const auto keep = ctx->saved_data["keep"].toIntVector();
+    const auto counts = ctx->saved_data["counts"].toIntVector();
+    const auto hyper = ctx->saved_data["hyper"].toDoubleVector();
+    const size_t K = counts.size();
+    const bool l2 = hyper[5] != 0.0, decay = l2 || hyper[6] != 0.0;
+    const variable_list saved = ctx->get_saved_variables();
+    const Tensor &new_mu = saved[0], &new_nu = saved[1];
+    Tensor dme = douts[K].defined() ? douts[K].contiguous() : Tensor();
+    Tensor dne = douts[K + 1].defined() ? douts[K + 1].contiguous() : Tensor();
+    const bool need_mu = ctx->needs_input_grad(2 * K), need_nu = ctx->needs_input_grad(2 * K + 1);
+    variable_list grads(2 * K + 6);  // dp_0.., dg_0.., dmu_flat, dnu_flat, then offs, keep, counts, hyper
+    // a leaf that receives no gradient at all leaves its range of dmu / dnu unwritten by the kernel: start from zeros
+    // whenever that can happen (some dp' missing, or skipped leaves), from uninitialised memory otherwise
+    auto fully_written = [&](const Tensor &dext) {  // will the kernel write the range of EVERY leaf?
+      if (!keep.empty()) return false;
+      if (dext.defined()) return true;
+      for (size_t k = 0; k < K; ++k)
+        if (!douts[k].defined()) return false;
+      return true;
+    };
+    Tensor dmu_flat, dnu_flat;
+    if (need_mu) dmu_flat = fully_written(dme) ? at::empty_like(new_mu) : at::zeros_like(new_mu);
+    if (need_nu) dnu_flat = fully_written(dne) ? at::empty_like(new_nu) : at::zeros_like(new_nu);
+    if (dmu_flat.defined() && dme.defined()) copy_ranges(dmu_flat, dme, keep);
+    if (dnu_flat.defined() && dne.defined()) copy_ranges(dnu_flat, dne, keep);
+    if (K == 0) {
+      grads[0] = dmu_flat, grads[1] = dnu_flat;
+      return grads;
+    }
+    const int dt = flat_family(saved[2], new_mu);
+    Ctx c(new_mu);
+    FlatAlloc fa;
+    std::vector<Tensor> cdp(K);
+    std::vector<long> slot_dg(K, -1), slot_dp(K, -1);
+    std::vector<size_t> live;
+    live.reserve(K);
+    for (size_t k = 0; k < K; ++k) {
+      const Tensor &g = saved[2 + k];
+      const bool hdp = douts[k].defined();
+      const bool need_p = ctx->needs_input_grad(k), need_g = ctx->needs_input_grad(K + k);
+      if (need_p && !decay) grads[k] = douts[k];  // p' = p + us: pass-through, no bytes move
+      if (!hdp && !dme.defined() && !dne.defined()) continue;
+      const bool wp = need_p && decay;
+      if (!need_g && !wp && !dmu_flat.defined() && !dnu_flat.defined()) continue;
+      if (hdp) cdp[k] = conform(douts[k], g), same_type(cdp[k], g);
+      if (need_g) slot_dg[k] = (long)fa.request(g);
+      if (wp) slot_dp[k] = (long)fa.request(g);
+      live.push_back(k);
+    }
+    fa.commit();
+    const size_t G = live.size();
+    FlatPtrs q(G);
+    for (size_t j = 0; j < G; ++j) {
+      const size_t k = live[j];
+      const Tensor &g = saved[2 + k];
+      if (slot_dg[k] >= 0) grads[K + k] = fa[slot_dg[k]];
+      if (slot_dp[k] >= 0) grads[k] = fa[slot_dp[k]];
+      q.dp[j] = cdp[k].defined() ? cdp[k].data_ptr() : nullptr;
+      q.mu[j] = at_offset(new_mu, offs[k]), q.nu[j] = at_offset(new_nu, offs[k]), q.g[j] = g.data_ptr();
+      q.dme[j] = at_offset(dme, offs[k]), q.dne[j] = at_offset(dne, offs[k]);
+      q.dg[j] = slot_dg[k] >= 0 ? grads[K + k].data_ptr() : nullptr;
+      // a moment gradient exists for this leaf iff something flows into it (dp' or the incoming moment gradient)
+      q.dmu[j] = (cdp[k].defined() || dme.defined()) ? (void *)at_offset(dmu_flat, offs[k]) : nullptr;
+      q.dnu[j] = (cdp[k].defined() || dne.defined()) ? (void *)at_offset(dnu_flat, offs[k]) : nullptr;
+      q.p[j] = l2 ? saved[2 + K + k].data_ptr() : nullptr;
+      q.dpo[j] = slot_dp[k] >= 0 ? grads[k].data_ptr() : nullptr;
+      q.n[j] = g.numel(), q.cnt[j] = (uint64_t)counts[k];
+    }
+    if (G > 0)
+      check(b200_adam_step_backward(dt, (int64_t)G, q.dp.data(), nullptr, q.mu.data(), q.nu.data(), q.g.data(),
+                                    q.dme.data(), q.dne.data(), q.dg.data(), q.dmu.data(), q.dnu.data(), q.p.data(),
+                                    q.dpo.data(), q.n.data(), q.cnt.data(), hyper[0], hyper[1], hyper[2], hyper[3], hyper[4],
+                                    hyper[5], hyper[6], hyper[7] != 0.0 ? 1 : 0, c.stream),
+            "flat_step backward");
+    grads[2 * K] = dmu_flat, grads[2 * K + 1] = dnu_flat;
+    return grads;
+  }
+};
+
+// Python entry point of the flat-state step.  `params` / `grads`: one entry per leaf of the group, `grads[i]` may be
+// None (leaf skipped this step: parameter returned as is, moments and count untouched).  `offsets[i]`: element offset
+// of leaf i in the flat moment buffers.  `counts[i]`: the step count AFTER this step for leaves with a gradient.
+// Returns (new_params, mu_flat', nu_flat').  `inplace`: parameters and flat moments are updated in place, no autograd
+// (Optimizer.step); gradients are overwritten with the scaled update unless keep_grads (the reference's side effect).
+std::tuple<std::vector<Tensor>, Tensor, Tensor> flat_step(const std::vector<Tensor> &params,
+                                                          const std::vector<OptTensor> &grads, const Tensor &mu_flat,
+                                                          const Tensor &nu_flat, const std::vector<int64_t> &offsets,
+                                                          const std::vector<int64_t> &counts, double b1, double b2,
+                                                          double eps, double eps_root, double step_size, double wd_l2,
+                                                          double wd_decoupled, bool maximize, bool inplace,
+                                                          bool keep_grads) {
+  const size_t L = params.size();
+  if (grads.size() != L || offsets.size() != L || counts.size() != L)
+    throw std::runtime_error("flat_step: params, grads, offsets and counts must have the same number of leaves");
+  std::vector<size_t> live;
+  std::vector<int64_t> keep;
+  for (size_t i = 0; i < L; ++i) {
+    if (grads[i].has_value()) {
+      live.push_back(i);
+    } else if (params[i].numel() > 0) {
+      keep.push_back(offsets[i]), keep.push_back(offsets[i] + params[i].numel());
+    }
+  }
+  const size_t K = live.size();
+  std::vector<Tensor> new_p(params);
+  const std::vector<double> hyper{b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize ? 1.0 : 0.0};
+  if (K == 0) return {new_p, mu_flat, nu_flat};
+  if (inplace) {
+    require_cuda(mu_flat);
+    const int dt = flat_family(params[live[0]], mu_flat);
+    Ctx c(mu_flat);
+    FlatPtrs q(K);
+    std::vector<Tensor> cg(K);
+    for (size_t k = 0; k < K; ++k) {
+      const size_t i = live[k];
+      const Tensor &p = params[i];
+      if (!p.is_contiguous() || flat_family(p, mu_flat) != dt || p.device() != mu_flat.device())
+        throw std::runtime_error("torchopt_b200: in-place step: parameters must be row-major tensors of one device and dtype");
+      cg[k] = conform(*grads[i], p);
+      q.po[k] = p.data_ptr(), q.dg[k] = cg[k].data_ptr();
+      q.muo[k] = at_offset(mu_flat, offsets[i]), q.nuo[k] = at_offset(nu_flat, offsets[i]);
+      q.n[k] = p.numel(), q.cnt[k] = (uint64_t)counts[i];
+    }
+    check(b200_adam_step_inplace_ex(dt, (int64_t)K, q.po.data(), q.dg.data(), q.muo.data(), q.nuo.data(), q.n.data(),
+                                    q.cnt.data(), b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize ? 1 : 0,
+                                    keep_grads ? 0 : 1, c.stream),
+          "flat_step (inplace)");
+    if (!keep_grads)
+      for (size_t k = 0; k < K; ++k) {
+        const Tensor &g = *grads[live[k]];
+        if (!cg[k].is_same(g)) const_cast<Tensor &>(g).copy_(cg[k]);
+      }
+    return {new_p, mu_flat, nu_flat};
+  }
+  std::vector<Tensor> flat;
+  std::vector<int64_t> offs(K), cnt(K);
+  flat.reserve(2 * K + 2);
+  for (size_t k = 0; k < K; ++k) flat.push_back(params[live[k]]), offs[k] = offsets[live[k]], cnt[k] = counts[live[k]];
+  for (size_t k = 0; k < K; ++k) flat.push_back(*grads[live[k]]);
+  flat.push_back(mu_flat), flat.push_back(nu_flat);
+  variable_list out = FlatStepNode::apply(at::TensorList(flat), offs, keep, cnt, hyper);
+  for (size_t k = 0; k < K; ++k) new_p[live[k]] = out[k];
+  return {new_p, out[K], out[K + 1]};
+}
+
 // Python entry points: all lists hold one tensor per leaf (no None: the callers filter leaves without a gradient)
 std::vector<Tensor> fused_autograd(const std::vector<Tensor> &updates, const std::vector<Tensor> &mu,
                                    const std::vector<Tensor> &nu, double b1, double b2, double eps, double eps_root,
@@ -871,6 +1119,12 @@ PYBIND11_MODULE(_C, mod) {
         py::arg("params"), py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("b1"), py::arg("b2"),
         py::arg("eps"), py::arg("eps_root"), py::arg("step_size"), py::arg("count"), py::arg("wd_l2") = 0.0,
         py::arg("wd_decoupled") = 0.0, py::arg("maximize") = false);
+  m.def("flat_step", &flat_step,
+        "whole Adam step with FLAT moment buffers (one node, 2K+2 autograd inputs): returns (new_params, mu', nu')",
+        py::arg("params"), py::arg("updates"), py::arg("mu_flat"), py::arg("nu_flat"), py::arg("offsets"),
+        py::arg("count"), py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("step_size"),
+        py::arg("wd_l2") = 0.0, py::arg("wd_decoupled") = 0.0, py::arg("maximize") = false,
+        py::arg("inplace") = false, py::arg("keep_grads") = false);
   m.def("host_step", &host_step, "Fused forward+backward over pinned HOST tensors (pipelined H2D/compute/D2H)",
         py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("dupdates"), py::arg("dmu_ext"), py::arg("dnu_ext"),
         py::arg("out"), py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("count"),

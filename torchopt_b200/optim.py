@@ -17,12 +17,16 @@ from torch import nn
 from torchopt_b200 import _pytree
 from torchopt_b200._native import adam_op
 from torchopt_b200.accelerated_op.adam_step import AdamStep
-from torchopt_b200.transform import (GradientTransformation, ScaleByAdamState, inc_count_flat,
-                                     scale_by_accelerated_adam)
+from torchopt_b200.accelerated_op.adam_op import INT64_MAX, capturing, count_as_int
+from torchopt_b200.transform import (STATE_DTYPE, GradientTransformation, ScaleByAdamState, inc_count_flat,
+                                     make_counts, scale_by_accelerated_adam)
 
 # A/B switch for parity tests: False makes MetaAdam / Adam run the chained transformations + apply_updates
 # (one Adam launch + 2 torch kernels per leaf per step) instead of the single whole-step launch.
 FUSE_STEP = True
+# A/B switch for parity tests: False keeps the optimizer state as per-leaf tensors (the reference's ScaleByAdamState
+# layout; 4L autograd inputs / 3L outputs per step) instead of the default flat moment buffers (2L+2 / L+2).
+FLAT_STATE = True
 
 
 def chain_flat(*transforms: GradientTransformation) -> GradientTransformation:
@@ -198,6 +202,193 @@ def _fused_chain_step(step_op: AdamStep, params: list, grads: list, state: tuple
     return new_params, (*state[:k], ScaleByAdamState(mu=new_mu, nu=new_nu, count=count_inc), *state[k + 1:])
 
 
+class _FlatGroup:
+    """The leaves of one (device, parameter dtype) group: where each lives in the flat moment buffers."""
+
+    __slots__ = ("index", "offsets", "numels", "shapes", "total", "device", "dtype", "state_dtype", "mu", "nu")
+
+    def __init__(self, index: list, leaves: Sequence[torch.Tensor]) -> None:
+        self.index = index
+        self.device, self.dtype = leaves[0].device, leaves[0].dtype
+        self.state_dtype = STATE_DTYPE.get(self.dtype, self.dtype)
+        align = max(1, 128 // torch.empty((), dtype=self.state_dtype).element_size())
+        self.numels = [p.numel() for p in leaves]
+        self.shapes = [p.shape for p in leaves]
+        self.offsets, total = [], 0
+        for k in self.numels:
+            self.offsets.append(total)
+            total = (total + k + align - 1) // align * align
+        self.total = total
+        self.mu = self.nu = None
+
+
+class FlatAdamState:
+    """Adam state of a fixed list of leaves with the moments of every (device, dtype) group in ONE buffer each and the
+    step counts as host integers -- the state layout ``MetaAdam`` / ``FuncAdam`` / ``Adam`` use by default.
+
+    Element for element it holds what the reference's ``ScaleByAdamState(mu, nu, count)`` holds
+    (transform/scale_by_adam.py:58-63) and ``to_leaf_state`` / ``from_leaf_state`` convert without arithmetic; a step
+    is one launch each way per group through ``adam_op.flat_step``: autograd sees 2L+2 inputs and L+2 outputs instead of
+    4L and 3L, no per-leaf count tensors are built, and the outputs of a step come from one allocation.  Leaves that get
+    no gradient in a step keep parameter, moments and count (the reference's skip semantics, adam_op.py:148-149)."""
+
+    def __init__(self, leaves: Sequence[torch.Tensor], moment_requires_grad: bool = False, *, _empty: bool = False):
+        self.num = len(leaves)
+        self.signature = [(p.shape, p.dtype, p.device) for p in leaves]
+        by_key: dict = {}
+        for i, p in enumerate(leaves):
+            by_key.setdefault((p.device, p.dtype), []).append(i)
+        self.groups = [_FlatGroup(idx, [leaves[i] for i in idx]) for idx in by_key.values()]
+        self.counts = [0] * self.num
+        self.in_capture = capturing()   # see accelerated_op.adam_op.check_capturable
+        if not _empty:
+            for gr in self.groups:
+                gr.mu = torch.zeros(gr.total, dtype=gr.state_dtype, device=gr.device, requires_grad=moment_requires_grad)
+                gr.nu = torch.zeros(gr.total, dtype=gr.state_dtype, device=gr.device, requires_grad=moment_requires_grad)
+
+    def matches(self, leaves: Sequence[torch.Tensor]) -> bool:
+        return len(leaves) == self.num and all(
+            p.shape == sig[0] and p.dtype == sig[1] and p.device == sig[2] for p, sig in zip(leaves, self.signature))
+
+    # pylint: disable-next=too-many-arguments
+    def step(self, hyper: tuple, params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor | None], *,
+             inplace: bool = False, keep_grads: bool = False) -> list:
+        """One whole optimizer step (recipe + Adam + scale + apply_updates); returns the new parameter list."""
+        if not self.in_capture and capturing():
+            # bias corrections are host scalars baked into the launch: same refusal as check_capturable
+            raise RuntimeError(
+                "torchopt_b200: an optimizer state created OUTSIDE a CUDA-graph capture is being stepped INSIDE one; every "
+                "replay would reuse the step count of the recording. Create the optimizer inside the captured function "
+                "(fresh state per replay, as in a MAML inner loop) or use capturable=True (Adam / AdamW / FlatAdam(W)).")
+        counts = self.counts
+        after = [c + (c != INT64_MAX) if g is not None else c for c, g in zip(counts, grads)]
+        b1, b2, eps, eps_root, step_size, wd_l2, wd_dec, maximize = hyper
+        if len(self.groups) == 1:
+            gr = self.groups[0]
+            new_p, gr.mu, gr.nu = adam_op.flat_step(list(params), list(grads), gr.mu, gr.nu, gr.offsets, after, b1, b2,
+                                                    eps, eps_root, step_size, wd_l2, wd_dec, maximize, inplace,
+                                                    keep_grads)
+        else:
+            new_p = list(params)
+            for gr in self.groups:
+                out, gr.mu, gr.nu = adam_op.flat_step(
+                    [params[i] for i in gr.index], [grads[i] for i in gr.index], gr.mu, gr.nu, gr.offsets,
+                    [after[i] for i in gr.index], b1, b2, eps, eps_root, step_size, wd_l2, wd_dec, maximize, inplace,
+                    keep_grads)
+                for i, t in zip(gr.index, out):
+                    new_p[i] = t
+        self.counts = after
+        return new_p
+
+    def to_leaf_state(self) -> ScaleByAdamState:
+        """The reference layout: per-leaf ``mu`` / ``nu`` (views of the flat buffers, differentiable) and per-leaf
+        0-dim int64 device ``count`` tensors tagged with their host value."""
+        mu, nu = [None] * self.num, [None] * self.num
+        devices = [None] * self.num
+        for gr in self.groups:
+            for i, off, k, shape in zip(gr.index, gr.offsets, gr.numels, gr.shapes):
+                mu[i] = gr.mu[off:off + k].view(shape)
+                nu[i] = gr.nu[off:off + k].view(shape)
+                devices[i] = gr.device
+        return ScaleByAdamState(mu=mu, nu=nu, count=make_counts(list(self.counts), devices))
+
+    @classmethod
+    def from_leaf_state(cls, leaves: Sequence[torch.Tensor], state: ScaleByAdamState) -> "FlatAdamState":
+        """Pack a reference-layout state (one differentiable ``cat`` per buffer, so gradients keep flowing to the
+        tensors the caller holds); counters are read from their host mirror (one sync each if they have none)."""
+        self = cls(leaves, _empty=True)
+        self.counts = [count_as_int(c) for c in state.count]
+        self.in_capture = all(getattr(c, "_b200_in_capture", True) for c in state.count) if self.num else capturing()
+        for gr in self.groups:
+            for name in ("mu", "nu"):
+                src, parts, end = getattr(state, name), [], 0
+                for i, off, k in zip(gr.index, gr.offsets, gr.numels):
+                    if off > end:
+                        parts.append(torch.zeros(off - end, dtype=gr.state_dtype, device=gr.device))
+                    if src[i].dtype != gr.state_dtype or src[i].numel() != k:
+                        raise ValueError("the loaded Adam state does not fit the parameters")
+                    parts.append(src[i].reshape(-1))
+                    end = off + k
+                if gr.total > end:
+                    parts.append(torch.zeros(gr.total - end, dtype=gr.state_dtype, device=gr.device))
+                setattr(gr, name, torch.cat(parts) if len(parts) > 1 else parts[0].contiguous())
+        return self
+
+    def stop_gradient_(self) -> None:
+        for gr in self.groups:
+            if gr.mu.grad_fn is not None:
+                gr.mu = gr.mu.detach().requires_grad_(True)
+            if gr.nu.grad_fn is not None:
+                gr.nu = gr.nu.detach().requires_grad_(True)
+
+
+class _AdamStateHolder:
+    """State plumbing shared by ``MetaAdam`` / ``FuncAdam`` / ``Adam``: the state lives EITHER in the flat layout
+    (``FlatAdamState``, fast path) OR as the chain's state tuple in the reference layout (what ``state`` /
+    ``state_dict()`` show and ``load_state_dict`` accepts).  Reading ``state`` converts flat -> reference layout without
+    arithmetic; the next step then re-packs from those very tensors (one ``cat`` per buffer), so gradients w.r.t. state
+    tensors the caller obtained keep flowing and in-place edits of them are honoured."""
+
+    impl: GradientTransformation
+    _flat: Any = None
+    _leaf: Any = None
+    _inplace_aliases = False     # in-place optimizers: the per-leaf views alias the flat buffers, both stay valid
+
+    def _chain_state(self, adam_state: ScaleByAdamState) -> tuple:
+        template = getattr(self, "_template", None)
+        if template is None:
+            template = self._template = self.impl.init([])
+        return tuple(adam_state if isinstance(st, ScaleByAdamState) else st for st in template)
+
+    @property
+    def state(self) -> Any:
+        if self._leaf is None and self._flat is not None:
+            self._leaf = self._chain_state(self._flat.to_leaf_state())
+        return self._leaf
+
+    @state.setter
+    def state(self, value: Any) -> None:
+        self._leaf, self._flat = value, None
+
+    def state_dict(self) -> Any:
+        return self.state
+
+    def load_state_dict(self, state: Any) -> None:
+        self.state = state
+
+    def _flat_state(self, leaves: list, moment_requires_grad: bool) -> FlatAdamState:
+        """The flat state for ``leaves``, converting from the reference layout if that is what is current."""
+        if self._leaf is not None and not (self._inplace_aliases and self._flat is not None):
+            adam_state = next(st for st in self._leaf if isinstance(st, ScaleByAdamState))
+            self._flat = FlatAdamState.from_leaf_state(leaves, adam_state)
+        elif self._flat is None:
+            self._flat = FlatAdamState(leaves, moment_requires_grad)
+        elif not self._flat.matches(leaves):
+            raise ValueError("the parameters changed shape / dtype / device since the optimizer state was created")
+        self._leaf = None
+        return self._flat
+
+    def _leaf_state(self, leaves: list) -> tuple:
+        """The chain's state tuple in the reference layout (A/B paths, schedules), creating it when there is none."""
+        state = self.state
+        if state is None:
+            state = self.impl.init(leaves)
+        self._leaf, self._flat = state, None
+        return state
+
+    def stop_gradient_(self) -> None:
+        """``torchopt.stop_gradient(optimizer)`` (utils.py:56-92): cut the state from its graph, keep requires_grad."""
+        if self._flat is not None and self._leaf is None:
+            self._flat.stop_gradient_()
+            return
+        if self._leaf is not None:
+            def cut(t: Any) -> Any:
+                if isinstance(t, torch.Tensor) and t.grad_fn is not None:
+                    return t.detach().requires_grad_(True)
+                return t
+            self.state = _pytree.tree_map(cut, self._leaf)
+
+
 class CapturableCounts:
     """Device-resident step counts + bias-correction tables for an in-place optimizer whose ``step()`` is recorded in a
     CUDA graph (``capturable=True``).  Nothing about the count is a host scalar any more: ``advance`` increments the
@@ -237,12 +428,13 @@ def _capturable_step(step_op: AdamStep, cap: CapturableCounts, params: list, gra
         step_size, wd_l2, wd_dec, maximize, step_op.keep_grads)
 
 
-class MetaAdam:
+class MetaAdam(_AdamStateHolder):
     """Differentiable Adam over an ``nn.Module`` (optim/meta/adam.py:33-92 + optim/meta/base.py:35-129).
 
     ``step(loss)`` takes ``autograd.grad(loss, params, create_graph=True)``, runs the fused Adam update
     out of place and rebinds the module's parameters to the new (non-leaf) tensors, so an outer loss can
-    back-propagate through the whole unroll.
+    back-propagate through the whole unroll.  By default the moments live in flat buffers (``FlatAdamState``): one
+    launch and one autograd node per step each way; ``state`` / ``state_dict()`` still show the reference layout.
     """
 
     DECOUPLED = False
@@ -258,37 +450,31 @@ class MetaAdam:
         self.step_op = (AdamStep(betas[0], betas[1], eps, eps_root=eps_root, step_size=-lr, weight_decay=weight_decay,
                                  decoupled=self.DECOUPLED, maximize=maximize) if self.fusable else None)
         self.module = module
+        self.moment_requires_grad = moment_requires_grad
         # (owner module, attribute name) for every parameter slot, in named_parameters order
         self.slots = [(m, name) for m in module.modules() for name, p in m._parameters.items() if p is not None]
-        self.state = None
 
     def params(self) -> list:
         return [m._parameters[name] for m, name in self.slots]
 
     def step(self, loss: torch.Tensor) -> None:
-        flat = self.params()
-        if self.state is None:
-            self.state = self.impl.init(flat)
+        flat = [m._parameters[name] for m, name in self.slots]
         grads = torch.autograd.grad(loss, flat, create_graph=True, allow_unused=True)
-        if self.fusable and FUSE_STEP:
-            new_params, self.state = _fused_chain_step(self.step_op, flat, list(grads), self.state)
+        if self.fusable and FUSE_STEP and FLAT_STATE:
+            new_params = self._flat_state(flat, self.moment_requires_grad).step(self.step_op.hyper, flat, grads)
+        elif self.fusable and FUSE_STEP:
+            new_params, self.state = _fused_chain_step(self.step_op, flat, list(grads), self._leaf_state(flat))
         else:
-            updates, self.state = self.impl.update(list(grads), self.state, params=flat, inplace=False)
+            updates, self.state = self.impl.update(list(grads), self._leaf_state(flat), params=flat, inplace=False)
             new_params = apply_updates(flat, updates, inplace=False)
         for (m, name), p in zip(self.slots, new_params):
             m._parameters[name] = p
 
-    def state_dict(self) -> Any:
-        return self.state
 
-    def load_state_dict(self, state: Any) -> None:
-        self.state = state
-
-
-class FuncAdam:
+class FuncAdam(_AdamStateHolder):
     """Functional Adam over explicit parameter lists (optim/func/base.py:36-120 + optim/func ``FuncAdam``):
     ``new_params = opt.step(loss, params)``.  ``apply_gradients`` is the same step for gradients already at hand.
-    Uses the single whole-step launch (weight decay and maximize folded in)."""
+    Uses the single whole-step launch (weight decay and maximize folded in) over flat moment buffers."""
 
     DECOUPLED = False
 
@@ -302,17 +488,23 @@ class FuncAdam:
         self.fusable = not callable(lr)
         self.hyper = dict(b1=betas[0], b2=betas[1], eps=eps, eps_root=eps_root, step_size=-lr if self.fusable else 0.0,
                           weight_decay=weight_decay, decoupled=self.DECOUPLED, maximize=maximize)
-        self.state = None
+        self.step_hyper = AdamStep(**self.hyper).hyper
+        self.moment_requires_grad = moment_requires_grad
 
     def apply_gradients(self, grads: Sequence, params: Sequence, inplace: bool = False) -> list:
         params = list(params)
-        if self.state is None:
-            self.state = self.impl.init(params)
+        if self.fusable and FUSE_STEP and FLAT_STATE:
+            flat = self._flat_state(params, self.moment_requires_grad)
+            if inplace:   # the raw parameter values are updated; the reference writes through p.data (update.py:71-74)
+                with torch.no_grad():
+                    flat.step(self.step_hyper, params, list(grads), inplace=True)
+                return params
+            return flat.step(self.step_hyper, params, list(grads))
         if self.fusable and FUSE_STEP:
             op = AdamStep(**self.hyper, inplace=inplace)
-            new_params, self.state = _fused_chain_step(op, params, list(grads), self.state)
+            new_params, self.state = _fused_chain_step(op, params, list(grads), self._leaf_state(params))
             return new_params
-        updates, self.state = self.impl.update(list(grads), self.state, params=params, inplace=inplace)
+        updates, self.state = self.impl.update(list(grads), self._leaf_state(params), params=params, inplace=inplace)
         return apply_updates(params, updates, inplace=inplace)
 
     def step(self, loss: torch.Tensor, params: Sequence, inplace: bool = False) -> list:
@@ -320,14 +512,8 @@ class FuncAdam:
         grads = torch.autograd.grad(loss, params, create_graph=not inplace, allow_unused=True)
         return self.apply_gradients(grads, params, inplace=inplace)
 
-    def state_dict(self) -> Any:
-        return self.state
 
-    def load_state_dict(self, state: Any) -> None:
-        self.state = state
-
-
-class Adam:
+class Adam(_AdamStateHolder):
     """In-place (non-differentiable) Adam over an iterable of parameters (optim/adam.py + optim/base.py:99-124)."""
 
     DECOUPLED = False
@@ -345,13 +531,18 @@ class Adam:
         self.fusable = not callable(lr)
         self.step_op = (AdamStep(betas[0], betas[1], eps, eps_root=eps_root, step_size=-lr, weight_decay=weight_decay,
                                  decoupled=self.DECOUPLED, maximize=maximize, inplace=True) if self.fusable else None)
-        self.state = self.impl.init(self.params)
         self.capturable = None
         if capturable:
             if not self.fusable:
                 raise NotImplementedError("capturable=True needs a constant learning rate")
+            self.state = self.impl.init(self.params)
             self.capturable = CapturableCounts(self.params, betas[0], betas[1])
             self._bind_capturable_counts()
+        elif self.fusable and FLAT_STATE and self.params:
+            self._inplace_aliases = True
+            self._flat_state(self.params, False)
+        else:
+            self.state = self.impl.init(self.params)
 
     def _adam_state_index(self) -> int:
         return next(i for i, st in enumerate(self.state) if isinstance(st, ScaleByAdamState))
@@ -377,10 +568,16 @@ class Adam:
         if self.capturable is not None:
             _capturable_step(self.step_op, self.capturable, self.params, grads, self.state[self._adam_state_index()])
             return
-        if self.fusable and FUSE_STEP:
-            _, self.state = _fused_chain_step(self.step_op, self.params, grads, self.state)
+        if self.fusable and FUSE_STEP and FLAT_STATE and self.params:
+            # a reference-layout view of the state that somebody read aliases the flat buffers, which are updated in
+            # place; only its count tensors go stale, so it is rebuilt on the next read.  A LOADED state is re-packed.
+            flat = self._flat if self._flat is not None else self._flat_state(self.params, False)
+            self._leaf = None
+            flat.step(self.step_op.hyper, self.params, grads, inplace=True)
+        elif self.fusable and FUSE_STEP:
+            _, self.state = _fused_chain_step(self.step_op, self.params, grads, self._leaf_state(self.params))
         else:
-            updates, self.state = self.impl.update(grads, self.state, params=self.params, inplace=True)
+            updates, self.state = self.impl.update(grads, self._leaf_state(self.params), params=self.params, inplace=True)
             apply_updates(self.params, updates, inplace=True)
 
 
