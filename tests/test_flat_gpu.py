@@ -34,6 +34,16 @@ def test_layout_offsets_pack_and_views_cpu():
         FlatLayout([torch.zeros(2), torch.zeros(2, dtype=torch.float64)])
 
 
+def test_padded_flat_layouts_refuse_zero_epsilons_cpu():
+    """eps == eps_root == 0 would turn the zero padding between leaves into 0/0 = NaN: refused up front."""
+    import torchopt_b200 as tb
+    net = nn.Linear(3, 2)
+    with pytest.raises(ValueError, match="padding"):
+        tb.FlatMetaAdam(net, lr=1e-3, eps=0.0, eps_root=0.0)
+    with pytest.raises(ValueError, match="padding"):
+        tb.FlatAdam(net.parameters(), lr=1e-3, eps=0.0)
+
+
 class Elementwise(nn.Module):
     """A 'network' made of element-wise maps only, so that the two layouts must agree bit for bit."""
 

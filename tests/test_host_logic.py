@@ -135,14 +135,18 @@ def _worker(rank: int, world: int, port: int, tmp: str):
         #     pre-scaled by 1/num_tasks == mean over the whole meta-batch.
         num_tasks = 7
         torch.manual_seed(0)
-        per_task = [[torch.randn(5, 3), torch.randn(11)] for _ in range(num_tasks)]   # same on every rank
-        local = [sum(per_task[t][k] for t in task_slice(num_tasks, rank, world)) for k in range(2)]
-        local.append(None)                                                            # an unused parameter
+        per_task = [[torch.randn(5, 3), torch.randn(11), torch.randn(4, dtype=torch.float64)]
+                    for _ in range(num_tasks)]                                        # same on every rank
+        local = [sum(per_task[t][k] for t in task_slice(num_tasks, rank, world)) for k in range(3)]
+        local.insert(2, None)                                                         # an unused parameter
         out = allreduce_meta_grads(local, scale=1.0 / num_tasks)
-        want = [torch.stack([per_task[t][k] for t in range(num_tasks)]).mean(0) for k in range(2)]
+        want = [torch.stack([per_task[t][k] for t in range(num_tasks)]).mean(0) for k in range(3)]
         assert out[2] is None
-        for a, b in zip(out[:2], want):
+        for a, b in zip(out[:2], want[:2]):
             torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-6)
+        # an fp64 meta-gradient is reduced in fp64 (its own bucket), not truncated to fp32
+        assert out[3].dtype == torch.float64
+        torch.testing.assert_close(out[3], want[2], rtol=1e-14, atol=1e-14)
         # (3) the same through GradBucket: .grad views of one flat buffer, backward accumulates in place,
         #     the all-reduce runs on the buffer itself
         from torchopt_b200.parallel import GradBucket

@@ -53,18 +53,21 @@ def test_host_step_equals_oracle(c_oracle, n, slice_elems, eps_root, count):
 
 @gpu
 def test_host_step_pageable_memory_and_argument_errors():
-    """Pageable (unpinned) host arrays work too (slower: the driver stages them); bad arguments raise."""
+    """Pageable (unpinned) host arrays are refused unless asked for (the driver stages them and the three streams of the
+    pipeline serialise), and then give the same results; bad arguments raise."""
     import torchopt_b200 as tb
     n = 50_000
     arrs = [torch.from_numpy(a) for a in _inputs(n, 1)]
     out = [torch.empty(n) for _ in range(6)]
-    tb.adam_op.host_step(*arrs, out, B1, B2, EPS, 0.0, 3, 16_384)
+    with pytest.raises(RuntimeError, match="page-locked"):
+        tb.adam_op.host_step(*arrs, out, B1, B2, EPS, 0.0, 3, 16_384)
+    tb.adam_op.host_step(*arrs, out, B1, B2, EPS, 0.0, 3, 16_384, allow_pageable=True)
     pinned_out = [torch.empty(n).pin_memory() for _ in range(6)]
     tb.adam_op.host_step(*[a.pin_memory() for a in arrs], pinned_out, B1, B2, EPS, 0.0, 3, 0)
     for a, b in zip(out, pinned_out):
         assert torch.equal(a, b)
     with pytest.raises(RuntimeError):
-        tb.adam_op.host_step(*arrs, [torch.empty(n - 1) for _ in range(6)], B1, B2, EPS, 0.0, 3, 0)
+        tb.adam_op.host_step(*arrs, [torch.empty(n - 1) for _ in range(6)], B1, B2, EPS, 0.0, 3, 0, allow_pageable=True)
     with pytest.raises(RuntimeError):
-        tb.adam_op.host_step(*[a.double() for a in arrs], out, B1, B2, EPS, 0.0, 3, 0)
+        tb.adam_op.host_step(*[a.double() for a in arrs], out, B1, B2, EPS, 0.0, 3, 0, allow_pageable=True)
     tb._C.host_release()

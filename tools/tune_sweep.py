@@ -26,6 +26,9 @@ L2_POLICIES = {"none": ("", ""), "ldEF": (".L2::evict_first", ""), "stEF": ("", 
 if os.environ.get("TUNE_ROUND", "2") == "1":   # round-1 sweep: vector width / unroll / CTA size
     VARIANTS = [(p, u, b, "none") for p, u in ((4, 1), (4, 2), (4, 4), (8, 1), (8, 2), (8, 4)) for b in (128, 256, 512)]
     RUNTIME = [(c, t) for c in (0, 1, 2, 4, 8, 16) for t in (1, 2, 4, 8)]
+elif os.environ.get("TUNE_ROUND", "2") == "3":  # mid-size leaves (2^20..2^26): CTA size / unroll vs the last-wave tail
+    VARIANTS = [(8, u, b, "none") for u in (1, 2) for b in (128, 256, 512)]
+    RUNTIME = [(0, 1), (4, 1), (8, 1), (16, 1)]
 else:                                         # round-2 sweep: L2 eviction priority on the best shapes
     VARIANTS = [(8, u, b, pol) for u in (1, 2) for b in (256, 512, 1024) for pol in L2_POLICIES]
     RUNTIME = [(0, 1), (0, 2), (16, 2), (32, 2)]

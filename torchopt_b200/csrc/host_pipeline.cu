@@ -22,20 +22,24 @@ struct Pipeline {
   cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
   cudaEvent_t e_h2d[NSLOT] = {}, e_comp[NSLOT] = {}, e_d2h[NSLOT] = {};
   bool ready = false;
+  std::mutex mu;  // one caller at a time per device; callers on different devices do not serialise
 
+  // Frees whatever exists (a creation that failed midway leaves a partial set: every handle is checked on its own).
   void destroy() {
-    if (!ready) return;
     for (int s = 0; s < NSLOT; ++s) {
-      for (int a = 0; a < NARR; ++a) cudaFree(buf[s][a]), buf[s][a] = nullptr;
-      cudaEventDestroy(e_h2d[s]), cudaEventDestroy(e_comp[s]), cudaEventDestroy(e_d2h[s]);
+      for (int a = 0; a < NARR; ++a)
+        if (buf[s][a]) cudaFree(buf[s][a]), buf[s][a] = nullptr;
+      if (e_h2d[s]) cudaEventDestroy(e_h2d[s]), e_h2d[s] = nullptr;
+      if (e_comp[s]) cudaEventDestroy(e_comp[s]), e_comp[s] = nullptr;
+      if (e_d2h[s]) cudaEventDestroy(e_d2h[s]), e_d2h[s] = nullptr;
     }
-    cudaStreamDestroy(s_h2d), cudaStreamDestroy(s_comp), cudaStreamDestroy(s_d2h);
+    if (s_h2d) cudaStreamDestroy(s_h2d), s_h2d = nullptr;
+    if (s_comp) cudaStreamDestroy(s_comp), s_comp = nullptr;
+    if (s_d2h) cudaStreamDestroy(s_d2h), s_d2h = nullptr;
     ready = false;
   }
 
-  int ensure(int dev, int64_t want_slice) {
-    if (ready && dev == device && want_slice == slice) return 0;
-    destroy();
+  int create(int dev, int64_t want_slice) {
     device = dev, slice = want_slice;
     cudaError_t e;
     for (int s = 0; s < NSLOT; ++s) {
@@ -51,40 +55,37 @@ struct Pipeline {
     ready = true;
     return 0;
   }
+
+  int ensure(int dev, int64_t want_slice) {
+    if (ready && dev == device && want_slice == slice) return 0;
+    destroy();
+    const int rc = create(dev, want_slice);
+    if (rc != 0) destroy();  // no partial pipeline survives a failed creation
+    return rc;
+  }
+
+  // After an error in the middle of a call copies may still be in flight into / out of the caller's host buffers:
+  // wait for them before the error is reported, so the caller may free or reuse its arrays.
+  void drain() {
+    if (s_h2d) cudaStreamSynchronize(s_h2d);
+    if (s_comp) cudaStreamSynchronize(s_comp);
+    if (s_d2h) cudaStreamSynchronize(s_d2h);
+  }
 };
 
-Pipeline g_pipe;
-std::mutex g_pipe_mu;
+constexpr int MAX_DEVICES = 64;
+Pipeline g_pipes[MAX_DEVICES];  // one per device
 
 }  // namespace
 
-#define CK(x)                          \
-  do {                                 \
-    cudaError_t _e = (x);              \
-    if (_e != cudaSuccess) return (int)_e; \
+#define CK(x)                                \
+  do {                                       \
+    cudaError_t _e = (x);                    \
+    if (_e != cudaSuccess) return (int)_e;   \
   } while (0)
 
-extern "C" int b200_adam_host_step_f32(const float *g, const float *mu, const float *nu, const float *du,
-                                       const float *dmu_ext, const float *dnu_ext, float *mu_out, float *nu_out,
-                                       float *u_out, float *dg, float *dmu, float *dnu, int64_t n, double b1,
-                                       double b2, double eps, double eps_root, uint64_t count,
-                                       int64_t slice_elems) {
-  if (n < 0) return B200_ADAM_E_ARG;
-  if (n == 0) return 0;
-  if (!g || !mu || !nu || !du || !dmu_ext || !dnu_ext || !mu_out || !nu_out || !u_out || !dg || !dmu || !dnu)
-    return B200_ADAM_E_ARG;
-  if (slice_elems <= 0) slice_elems = 1 << 22;  // 16 MiB per array per slice
-  if (slice_elems > n) slice_elems = (n + 7) & ~int64_t(7);
-  slice_elems = (slice_elems + 7) & ~int64_t(7);
-
-  std::lock_guard<std::mutex> lock(g_pipe_mu);
-  int dev = 0;
-  CK(cudaGetDevice(&dev));
-  if (int rc = g_pipe.ensure(dev, slice_elems)) return rc;
-  Pipeline &p = g_pipe;
-
-  const float *h_in[6] = {g, mu, nu, du, dmu_ext, dnu_ext};
-  float *h_out[6] = {mu_out, nu_out, u_out, dg, dmu, dnu};
+static int host_step_locked(Pipeline &p, const float *const h_in[6], float *const h_out[6], int64_t n, double b1,
+                            double b2, double eps, double eps_root, uint64_t count, int64_t slice_elems) {
   int64_t k = 0;
   for (int64_t off = 0; off < n; off += slice_elems, ++k) {
     const int s = (int)(k % NSLOT);
@@ -117,9 +118,43 @@ extern "C" int b200_adam_host_step_f32(const float *g, const float *mu, const fl
   return 0;
 }
 
-// Frees the staging buffers/streams of b200_adam_host_step_f32 (optional; they are reused across calls).
+extern "C" int b200_adam_host_step_f32(const float *g, const float *mu, const float *nu, const float *du,
+                                       const float *dmu_ext, const float *dnu_ext, float *mu_out, float *nu_out,
+                                       float *u_out, float *dg, float *dmu, float *dnu, int64_t n, double b1,
+                                       double b2, double eps, double eps_root, uint64_t count,
+                                       int64_t slice_elems) {
+  if (n < 0) return B200_ADAM_E_ARG;
+  if (n == 0) return 0;
+  if (!g || !mu || !nu || !du || !dmu_ext || !dnu_ext || !mu_out || !nu_out || !u_out || !dg || !dmu || !dnu)
+    return B200_ADAM_E_ARG;
+  if (slice_elems <= 0) slice_elems = 1 << 22;  // 16 MiB per array per slice
+  if (slice_elems > n) slice_elems = (n + 7) & ~int64_t(7);
+  slice_elems = (slice_elems + 7) & ~int64_t(7);
+
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEVICES) return B200_ADAM_E_NO_DEVICE;
+  Pipeline &p = g_pipes[dev];
+  std::lock_guard<std::mutex> lock(p.mu);
+  if (int rc = p.ensure(dev, slice_elems)) return rc;
+  const float *h_in[6] = {g, mu, nu, du, dmu_ext, dnu_ext};
+  float *h_out[6] = {mu_out, nu_out, u_out, dg, dmu, dnu};
+  const int rc = host_step_locked(p, h_in, h_out, n, b1, b2, eps, eps_root, count, slice_elems);
+  if (rc != 0) p.drain();  // nothing of this call may still touch the caller's buffers when the error is reported
+  return rc;
+}
+
+// Frees the staging buffers/streams of b200_adam_host_step_f32 on every device (optional; they are reused across calls).
 extern "C" int b200_adam_host_release(void) {
-  std::lock_guard<std::mutex> lock(g_pipe_mu);
-  g_pipe.destroy();
+  int cur = 0;
+  const bool have_cur = cudaGetDevice(&cur) == cudaSuccess;
+  for (int d = 0; d < MAX_DEVICES; ++d) {
+    Pipeline &p = g_pipes[d];
+    std::lock_guard<std::mutex> lock(p.mu);
+    if (p.device < 0) continue;
+    if (cudaSetDevice(p.device) == cudaSuccess) p.destroy();
+    p.device = -1;
+  }
+  if (have_cur) cudaSetDevice(cur);
   return 0;
 }

@@ -197,13 +197,13 @@ inline void require_inplace_layout(const Tensor &t, const Tensor &donor, const c
 // FlatAlloc hands out every output of a call from ONE buffer per (device, dtype): each output has its donor's sizes
 // and (for dense donors) strides -- exactly what empty_like gives -- and starts on a 128-byte boundary.
 // The outputs are independent tensors sharing a storage (Tensor::set_), not autograd views of each other.
-// Only SMALL outputs are pooled (< kPoolMaxBytes each): a pooled output keeps the whole pool alive, which is harmless
+// Only SMALL outputs are pooled (< kPoolMaxBytes = 256 KiB each): a pooled output keeps the whole pool alive, which is harmless
 // for the many tiny leaves the pool exists for (41 of ResNet-18's 62 leaves are < 4096 elements) but would let one
 // surviving 64-element tensor pin hundreds of MB if large leaves shared its storage.  Large outputs get their own
 // allocation (the allocator cost is noise next to their kernel time).
 class FlatAlloc {
  public:
-  static constexpr int64_t kPoolMaxBytes = 1 << 20;
+  static constexpr int64_t kPoolMaxBytes = 256 << 10;
   size_t request(const Tensor &donor) {
     reqs_.push_back(&donor);
     return reqs_.size() - 1;
@@ -1044,9 +1044,15 @@ std::vector<Tensor> step_autograd(const std::vector<Tensor> &params, const std::
 // host-buffer step (CPU tensors in, CPU tensors out, work done on the current CUDA device)
 std::array<Tensor, 6> host_step(const Tensor &g, const Tensor &mu, const Tensor &nu, const Tensor &du,
                                 const Tensor &dmu_ext, const Tensor &dnu_ext, std::array<Tensor, 6> out, double b1,
-                                double b2, double eps, double eps_root, size_t count, int64_t slice_elems) {
+                                double b2, double eps, double eps_root, size_t count, int64_t slice_elems,
+                                bool allow_pageable) {
   const Tensor *ins[6] = {&g, &mu, &nu, &du, &dmu_ext, &dnu_ext};
   for (int a = 0; a < 6; ++a) {
+    // cudaMemcpyAsync from / to pageable memory is staged through the driver's own bounce buffer and serialises the
+    // three streams of the pipeline: refuse it unless the caller says that is acceptable
+    if (!allow_pageable && (!ins[a]->is_pinned() || !out[a].is_pinned()))
+      throw std::runtime_error("host_step: expects page-locked (pin_memory()) CPU tensors; pass allow_pageable=True to "
+                               "accept pageable ones at a fraction of the link rate");
     if (!ins[a]->device().is_cpu() || !out[a].device().is_cpu() || ins[a]->scalar_type() != at::kFloat ||
         out[a].scalar_type() != at::kFloat || !ins[a]->is_contiguous() || !out[a].is_contiguous() ||
         ins[a]->numel() != g.numel() || out[a].numel() != g.numel())
@@ -1128,7 +1134,7 @@ PYBIND11_MODULE(_C, mod) {
   m.def("host_step", &host_step, "Fused forward+backward over pinned HOST tensors (pipelined H2D/compute/D2H)",
         py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("dupdates"), py::arg("dmu_ext"), py::arg("dnu_ext"),
         py::arg("out"), py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("count"),
-        py::arg("slice_elems") = 0);
+        py::arg("slice_elems") = 0, py::arg("allow_pageable") = false);
   // -- utilities
   mod.def("kernel_launches", []() { return b200_adam_kernel_launches(); });
   mod.def("abi_version", []() { return b200_adam_abi_version(); });

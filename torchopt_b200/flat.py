@@ -91,6 +91,17 @@ class FlatLayout:
         return [flat[o:o + k].view(shape) for o, k, shape in zip(self.offsets, self.numels, self.shapes)]
 
 
+def _check_padding_safe(eps: float, eps_root: float) -> None:
+    """``FlatMetaAdam`` / ``FlatAdam`` launch ONE range over the whole buffer, padding included.  Padding holds
+    g = mu = nu = 0, for which the update is 0 / (sqrt(0 + eps_root) + eps): exactly 0 unless both epsilons are 0, when it
+    is NaN -- and a NaN in the padding of the flat parameters would poison every whole-buffer reduction (norms, clipping,
+    an all-reduce sanity check).  (The default optimizers -- ``MetaAdam`` / ``Adam`` over ``FlatAdamState`` -- launch per
+    leaf range and never touch padding.)"""
+    if eps == 0.0 and eps_root == 0.0:
+        raise ValueError("FlatMetaAdam / FlatAdam need eps > 0 or eps_root > 0: with both zero the update of the zero "
+                         "padding between leaves is 0/0 = NaN (use MetaAdam / Adam, which never touch padding)")
+
+
 def _module_slots(module: nn.Module) -> list:
     return [(m, name) for m in module.modules() for name, p in m._parameters.items() if p is not None]
 
@@ -117,6 +128,7 @@ class FlatMetaAdam:
                  moment_requires_grad: bool = True, maximize: bool = False, use_accelerated_op: bool = True) -> None:
         if callable(lr):
             raise NotImplementedError("learning-rate schedules are outside the scope of torchopt_b200")
+        _check_padding_safe(eps, eps_root)
         recipe = adamw if self.DECOUPLED else adam
         self.impl = recipe(lr, betas, eps, weight_decay, eps_root=eps_root, moment_requires_grad=moment_requires_grad,
                            maximize=maximize, use_accelerated_op=use_accelerated_op)
@@ -206,6 +218,7 @@ class FlatAdam:
         the rest of a training iteration (``zero_grad`` + forward + backward + ``step``); each replay is a real step."""
         if callable(lr):
             raise NotImplementedError("learning-rate schedules are outside the scope of torchopt_b200")
+        _check_padding_safe(eps, eps_root)
         self.params = list(params)
         recipe = adamw if self.DECOUPLED else adam
         self.impl = recipe(lr, betas, eps, weight_decay, eps_root=eps_root, maximize=maximize,

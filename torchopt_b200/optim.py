@@ -27,6 +27,9 @@ FUSE_STEP = True
 # A/B switch for parity tests: False keeps the optimizer state as per-leaf tensors (the reference's ScaleByAdamState
 # layout; 4L autograd inputs / 3L outputs per step) instead of the default flat moment buffers (2L+2 / L+2).
 FLAT_STATE = True
+# Measurement hook (bench.py): when True, MetaAdam.step records in ``last_host_us`` how its host time splits between
+# ``autograd.grad`` of the caller's loss and the optimizer update proper.
+PROFILE_HOST = False
 
 
 def chain_flat(*transforms: GradientTransformation) -> GradientTransformation:
@@ -459,7 +462,12 @@ class MetaAdam(_AdamStateHolder):
 
     def step(self, loss: torch.Tensor) -> None:
         flat = [m._parameters[name] for m, name in self.slots]
+        if PROFILE_HOST:
+            import time
+            h0 = time.perf_counter()
         grads = torch.autograd.grad(loss, flat, create_graph=True, allow_unused=True)
+        if PROFILE_HOST:
+            h1 = time.perf_counter()
         if self.fusable and FUSE_STEP and FLAT_STATE:
             new_params = self._flat_state(flat, self.moment_requires_grad).step(self.step_op.hyper, flat, grads)
         elif self.fusable and FUSE_STEP:
@@ -469,6 +477,8 @@ class MetaAdam(_AdamStateHolder):
             new_params = apply_updates(flat, updates, inplace=False)
         for (m, name), p in zip(self.slots, new_params):
             m._parameters[name] = p
+        if PROFILE_HOST:
+            self.last_host_us = ((h1 - h0) * 1e6, (time.perf_counter() - h1) * 1e6)
 
 
 class FuncAdam(_AdamStateHolder):

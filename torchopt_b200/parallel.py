@@ -63,7 +63,7 @@ def task_slice(num_tasks: int, rank: int, world: int) -> range:
 
 def allreduce_meta_grads(grads: Sequence[torch.Tensor | None], *, scale: float | None = None,
                          group: dist.ProcessGroup | None = None) -> list[torch.Tensor | None]:
-    """Sum meta-gradients over ranks with a single all-reduce of one flattened bucket, in place.
+    """Sum meta-gradients over ranks with a single all-reduce of one flattened bucket per (device, dtype), in place.
 
     ``scale`` (e.g. ``1 / num_tasks``) is applied BEFORE the reduction, reproducing the reference's
     ``torch.mean(torch.stack(task_losses))`` (examples/few-shot/maml_omniglot.py:175) when every rank contributes
@@ -73,16 +73,26 @@ def allreduce_meta_grads(grads: Sequence[torch.Tensor | None], *, scale: float |
     live = [g for g in grads if g is not None]
     if not live:
         return list(grads)
-    bucket = torch.cat([g.reshape(-1).to(torch.float32) for g in live])
-    if scale is not None:
-        bucket.mul_(scale)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
-    off = 0
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not multi:                       # world size 1: nothing to exchange, no flatten / copy-back
+        if scale is not None:
+            for g in live:
+                g.mul_(scale)
+        return list(grads)
+    # one bucket per (device, dtype) -- normally exactly one; fp64 meta-gradients are reduced in fp64, not truncated
+    groups: dict = {}
     for g in live:
-        k = g.numel()
-        g.copy_(bucket[off:off + k].view_as(g))
-        off += k
+        groups.setdefault((g.device, g.dtype), []).append(g)
+    for members in groups.values():
+        bucket = torch.cat([g.reshape(-1) for g in members])
+        if scale is not None:
+            bucket.mul_(scale)
+        dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
+        off = 0
+        for g in members:
+            k = g.numel()
+            g.copy_(bucket[off:off + k].view_as(g))
+            off += k
     return list(grads)
 
 
