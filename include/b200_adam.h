@@ -196,6 +196,34 @@ int b200_adam_step_backward(int dtype, int64_t num_leaves, const void *const *dp
                             const uint64_t *count, double b1, double b2, double eps, double eps_root, double step_size,
                             double wd_l2, double wd_decoupled, int maximize, void *stream);
 
+/* Capturable DIFFERENTIABLE step (forward + backward): b200_adam_step_forward / b200_adam_step_backward with the step
+ * counts in device memory and all bias corrections in device tables, so that a differentiable optimizer step over a
+ * PERSISTENT state (MetaAdam / FuncAdam(capturable=True)) can be recorded in a CUDA graph and every replay is one real
+ * step (the reference reads `count` back to the host on every call, accelerated_op/adam_op.py:98-101,110).
+ *   count_dev[i]   DEVICE pointer to the int64 step count of leaf i (already incremented); the backward must be given
+ *                  the same value the forward saw (the binding snapshots it per step);
+ *   c1 / c2 tables as for b200_adam_step_inplace_capturable; the backward additionally needs o1 = 1-b1^count and
+ *                  c2e = 1/(1-b2^count+eps_root).  b200_adam_bias_table_len_ex gives the length from which ALL FOUR have
+ *                  reached their limit value, b200_adam_bias_table_ex fills the four host tables with the same std::pow
+ *                  expressions (one rounding) as the host-scalar entry points: results are bit-identical to those. */
+int64_t b200_adam_bias_table_len_ex(int dtype, double b1, double b2, double eps_root);
+int b200_adam_bias_table_ex(int dtype, double b1, double b2, double eps_root, int64_t len, void *c1_host, void *c2_host,
+                            void *o1_host, void *c2e_host);
+int b200_adam_step_forward_capturable(int dtype, int64_t num_leaves, const void *const *p, const void *const *g,
+                                      const void *const *mu, const void *const *nu, void *const *p_out,
+                                      void *const *mu_out, void *const *nu_out, void *const *us_out, const int64_t *n,
+                                      const int64_t *const *count_dev, const void *c1_table_dev, const void *c2_table_dev,
+                                      int64_t table_len, double b1, double b2, double eps, double eps_root,
+                                      double step_size, double wd_l2, double wd_decoupled, int maximize, void *stream);
+int b200_adam_step_backward_capturable(int dtype, int64_t num_leaves, const void *const *dp, const void *const *dus,
+                                       const void *const *new_mu, const void *const *new_nu, const void *const *g,
+                                       const void *const *dmu_ext, const void *const *dnu_ext, void *const *dg,
+                                       void *const *dmu, void *const *dnu, const void *const *p, void *const *dp_out,
+                                       const int64_t *n, const int64_t *const *count_dev, const void *c1_table_dev,
+                                       const void *c2_table_dev, const void *o1_table_dev, const void *c2e_table_dev,
+                                       int64_t table_len, double b1, double b2, double eps, double eps_root,
+                                       double step_size, double wd_l2, double wd_decoupled, int maximize, void *stream);
+
 /* ---- host-buffer entry point (what an application holding HOST arrays calls; used for the e2e number) */
 
 /* One fused differentiable forward + backward over HOST arrays of n elements (dtype F32 only):

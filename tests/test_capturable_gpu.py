@@ -154,3 +154,124 @@ def test_training_iteration_recorded_in_a_cuda_graph(flat):
     assert torch.equal(la, lb)
     for p, q in zip(net_a.parameters(), net_b.parameters()):
         assert torch.equal(p, q)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# capturable DIFFERENTIABLE step (round 2): MetaAdam / FuncAdam(capturable=True) over a persistent state
+# ---------------------------------------------------------------------------------------------------------------
+def test_bias_tables_ex_match_the_reference_expressions():
+    """[c1, c2, o1, c2e]: the four host expressions of the reference launchers (adam_op_impl_cuda.cu:73-75,452-454), one
+    rounding each; the tables end where all four have reached their limit values."""
+    import math
+
+    import torchopt_b200 as tb
+    for family, dt in ((0, np.float32), (1, np.float64)):
+        for b1, b2, er in ((0.9, 0.999, 0.0), (0.9, 0.999, 1e-8), (0.5, 0.6, 1e-3)):
+            c1, c2, o1, c2e = (t.numpy() for t in tb.adam_op.bias_tables_ex(family, b1, b2, er))
+            n = len(c1)
+            cs = range(1, n + 1)
+            assert_bits_equal(c1, np.array([dt(1 / (1 - math.pow(b1, c))) for c in cs], dtype=dt), "c1")
+            assert_bits_equal(c2, np.array([dt(1 / (1 - math.pow(b2, c))) for c in cs], dtype=dt), "c2")
+            assert_bits_equal(o1, np.array([dt(1 - math.pow(b1, c)) for c in cs], dtype=dt), "o1")
+            assert_bits_equal(c2e, np.array([dt(1 / (1 - math.pow(b2, c) + er)) for c in cs], dtype=dt), "c2e")
+            for c in (n + 1, 10 * n, 10**9):    # every larger count reproduces the last entry
+                assert dt(1 / (1 - math.pow(b1, c))) == c1[-1] and dt(1 / (1 - math.pow(b2, c))) == c2[-1]
+                assert dt(1 - math.pow(b1, c)) == o1[-1] and dt(1 / (1 - math.pow(b2, c) + er)) == c2e[-1]
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(weight_decay=1e-2), dict(weight_decay=1e-2, maximize=True)],
+                         ids=["adam", "l2", "l2_max"])
+@pytest.mark.parametrize("mrg", [False, True])
+def test_capturable_differentiable_step_eager_equals_host_scalar_path(kw, mrg):
+    """Eager (no graph): the device-count + table form gives the same parameters, moments and gradients as the default
+    host-scalar form, step after step, including a leaf that is skipped in some steps (its count must not advance)."""
+    import torchopt_b200 as tb
+    gen = torch.Generator("cuda").manual_seed(21)
+    p0 = [torch.randn(k, device="cuda", generator=gen) * 0.3 for k in SIZES]
+    ws = [[torch.rand(k, device="cuda", generator=gen) + 0.5 for k in SIZES] for _ in range(5)]
+
+    def run(capturable):
+        opt = tb.FuncAdam(1e-2, eps_root=1e-8, moment_requires_grad=mrg, capturable=capturable, **kw)
+        cur = [p.clone() for p in p0]
+        out = []
+        for k in range(5):
+            leaves = [p.detach().requires_grad_(True) for p in cur]
+            hyper = [w.clone().requires_grad_(True) for w in ws[k]]
+            grads = [w * p for w, p in zip(hyper, leaves)]
+            if k in (1, 3):
+                grads[2] = None                       # skipped leaf: parameter, moments and count stay
+            new_p = opt.apply_gradients(grads, leaves)
+            outer = sum((q * q).sum() for q in new_p)
+            meta = torch.autograd.grad(outer, hyper + leaves, allow_unused=True)
+            cur = [q.detach() for q in new_p]
+            tb.stop_gradient(opt)                     # the capturable state is carried by value: same cut here
+            out.append((cur, meta))
+        st = next(s for s in opt.state if isinstance(s, tb.ScaleByAdamState))
+        torch.cuda.synchronize()
+        return out, [m.detach().clone() for m in st.mu], [int(c) for c in st.count]
+
+    a, mu_a, cnt_a = run(True)
+    b, mu_b, cnt_b = run(False)
+    assert cnt_a == cnt_b == [5, 5, 3, 5, 5]
+    for (cur_a, meta_a), (cur_b, meta_b) in zip(a, b):
+        for x, y in zip(cur_a + list(meta_a), cur_b + list(meta_b)):
+            assert (x is None) == (y is None)
+            if x is not None:
+                assert torch.equal(x, y)
+    for x, y in zip(mu_a, mu_b):
+        assert torch.equal(x, y)
+
+
+def test_differentiable_step_with_persistent_state_recorded_in_a_cuda_graph():
+    """K replays of ONE captured differentiable step (persistent FuncAdam(capturable=True) state, parameters in static
+    buffers, meta-gradient w.r.t. a hyper-parameter taken inside the graph) == K eager steps, bit for bit.  The
+    reference cannot be recorded at all (count -> host on every call, accelerated_op/adam_op.py:98-101); without
+    capturable=True this package refuses (test_flat_state_gpu.py) because the bias corrections would be frozen."""
+    import torchopt_b200 as tb
+    gen = torch.Generator("cuda").manual_seed(31)
+    p0 = [torch.randn(k, device="cuda", generator=gen) * 0.3 for k in SIZES]
+    w0 = [torch.rand(k, device="cuda", generator=gen) + 0.5 for k in SIZES]
+    K, WARM = 6, 3     # graphs.capture runs the function WARM times eagerly before recording: those are real steps too
+
+    def make():
+        params = [p.clone() for p in p0]                                    # static parameter buffers
+        hyper = [w.clone().requires_grad_(True) for w in w0]
+        return params, hyper
+
+    # eager reference: K + WARM + 1 (the recording itself does not execute) steps of the host-scalar optimizer
+    params, hyper = make()
+    opt = tb.FuncAdam(1e-2, eps_root=1e-8, weight_decay=1e-2)
+    want = []
+    for _ in range(WARM + K):
+        leaves = [p.detach().requires_grad_(True) for p in params]
+        new_p = opt.apply_gradients([w * p for w, p in zip(hyper, leaves)], leaves)
+        meta = torch.autograd.grad(sum((q * q).sum() for q in new_p), hyper)
+        with torch.no_grad():
+            for p, q in zip(params, new_p):
+                p.copy_(q)
+        tb.stop_gradient(opt)
+        want.append(([p.clone() for p in params], [m.clone() for m in meta]))
+
+    params, hyper = make()
+    opt_c = tb.FuncAdam(1e-2, eps_root=1e-8, weight_decay=1e-2, capturable=True)
+
+    def one_step():
+        leaves = [p.detach().requires_grad_(True) for p in params]
+        new_p = opt_c.apply_gradients([w * p for w, p in zip(hyper, leaves)], leaves)
+        meta = torch.autograd.grad(sum((q * q).sum() for q in new_p), hyper)
+        with torch.no_grad():
+            for p, q in zip(params, new_p):
+                p.copy_(q)                                                  # persistent parameters: static addresses
+        return meta
+
+    step = tb.graphs.capture(one_step, warmup=WARM)
+    got = []
+    for _ in range(K):
+        meta = step()
+        torch.cuda.synchronize()
+        got.append(([p.clone() for p in params], [m.clone() for m in meta]))
+    for k in range(K):
+        for x, y in zip(got[k][0] + got[k][1], want[WARM + k][0] + want[WARM + k][1]):
+            assert torch.equal(x, y), f"replay {k} differs from eager step {WARM + k + 1}"
+    st = next(s for s in opt_c.state if isinstance(s, tb.ScaleByAdamState))
+    assert [int(c) for c in st.count] == [WARM + K] * len(SIZES)

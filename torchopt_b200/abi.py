@@ -50,6 +50,16 @@ SYMBOLS = {
     "b200_adam_step_inplace_capturable": (c_int, [c_int, c_int64, _vpp, _vpp, _vpp, _vpp, _i64p, _vpp, c_void_p,
                                                   c_void_p, c_int64, c_double, c_double, c_double, c_double, c_double,
                                                   c_double, c_double, c_int, c_int, c_void_p]),
+    "b200_adam_bias_table_len_ex": (c_int64, [c_int, c_double, c_double, c_double]),
+    "b200_adam_bias_table_ex": (c_int, [c_int, c_double, c_double, c_double, c_int64, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]),
+    "b200_adam_step_forward_capturable": (c_int, [c_int, c_int64, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _i64p,
+                                                  _vpp, c_void_p, c_void_p, c_int64, c_double, c_double, c_double,
+                                                  c_double, c_double, c_double, c_double, c_int, c_void_p]),
+    "b200_adam_step_backward_capturable": (c_int, [c_int, c_int64, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp,
+                                                   _vpp, _vpp, _vpp, _i64p, _vpp, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                   c_int64, c_double, c_double, c_double, c_double, c_double, c_double,
+                                                   c_double, c_int, c_void_p]),
     "b200_adam_step_backward": (c_int, [c_int, c_int64, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp, _vpp,
                                         _vpp, _vpp, _i64p, _u64p, c_double, c_double, c_double, c_double, c_double,
                                         c_double, c_double, c_int, c_void_p]),

@@ -182,8 +182,15 @@ __device__ __forceinline__ void load_pack(Pack<T, P> &r, const T *p) {
 // streams that are absent in a launch leave their Pack untouched; zero it so the compiler keeps it in registers
 template <typename T, int P>
 __device__ __forceinline__ void zero_pack(Pack<T, P> &r) {
+  if constexpr (sizeof(T) * P < 4) {
+    // a sub-word pack (one bf16 element on the scalar path): zero it through its own type -- writing the 32-bit word
+    // of the union and reading 16 bits back makes the compiler park the pack in local memory
 #pragma unroll
-  for (int k = 0; k < (int)((sizeof(T) * P + 3) / 4); ++k) r.w[k] = 0u;
+    for (int k = 0; k < P; ++k) r.v[k] = T();
+  } else {
+#pragma unroll
+    for (int k = 0; k < (int)((sizeof(T) * P + 3) / 4); ++k) r.w[k] = 0u;
+  }
 }
 
 template <bool NC, typename T, int P>
@@ -438,12 +445,27 @@ __device__ __forceinline__ CT rd(CT x) {
   return up<CT>(Down<TG, CT>::cvt(x));
 }
 
+// Capturable form of the step kernels (for a step recorded in a CUDA graph: the in-place training step of Adam /
+// FlatAdam(capturable=True) and the differentiable step of MetaAdam / FuncAdam(capturable=True)): nothing about the
+// step count may be baked into the launch, so
+//   * the count is read from DEVICE memory (an int64 the caller increments on the device), and
+//   * the bias corrections C1 = 1/(1-b1^c), C2 = 1/(1-b2^c) (forward, backward) and O1 = 1-b1^c,
+//     C2E = 1/(1-b2^c+eps_root) (backward) come from device TABLES indexed by the count.  The tables are filled on the
+//     host with the very expressions the host-scalar launchers use (std::pow in double, one rounding to CT), so results
+//     stay bit-identical; they end where every correction has reached its limit value in CT (count 16 628 for
+//     b2 = 0.999 in fp32), and larger counts clamp to the last entry.  `flags` of the table carries the table length.
+__device__ __forceinline__ int bias_index(const void *count_ptr, int len) {
+  const long long c = *(const long long *)count_ptr;
+  return c < 1 ? 0 : (c > (long long)len ? len - 1 : (int)c - 1);
+}
+
 template <typename TG_, typename TS_, typename CT_, bool INPLACE>
 struct StepFwd {
   using TG = TG_;
   using TS = TS_;
   using CT = CT_;
-  static constexpr int NPTR = 8, NGS = 10, NLS = 2;
+  // ptr[8..10] (optional, NULL = host scalars): capturable form -- see bias_index below
+  static constexpr int NPTR = 11, NGS = 10, NLS = 2;
   struct Leaf {
     const TG *p, *g;
     const TS *mu, *nu;
@@ -459,7 +481,12 @@ struct StepFwd {
     L.p_o = (TG *)t.ptr[4][l], L.mu_o = (TS *)t.ptr[5][l], L.nu_o = (TS *)t.ptr[6][l], L.us_o = (TG *)t.ptr[7][l];
     L.B1 = t.gs[0], L.OMB1 = t.gs[1], L.B2 = t.gs[2], L.OMB2 = t.gs[3], L.ER = t.gs[4], L.EPS = t.gs[5];
     L.S = t.gs[6], L.WD1 = t.gs[7], L.WD2 = t.gs[8], L.SGN = t.gs[9];
-    L.C1 = t.ls[0][l], L.C2 = t.ls[1][l];
+    if (t.ptr[8][l] != nullptr) {
+      const int idx = bias_index(t.ptr[8][l], t.flags);
+      L.C1 = ((const CT *)t.ptr[9][l])[idx], L.C2 = ((const CT *)t.ptr[10][l])[idx];
+    } else {
+      L.C1 = t.ls[0][l], L.C2 = t.ls[1][l];
+    }
     return L;
   }
   template <int P>
@@ -509,32 +536,6 @@ struct StepFwd {
   }
 };
 
-// Capturable in-place step (for an optimizer step recorded in a CUDA graph together with the forward / backward of a
-// training iteration): nothing about the step count may be baked into the launch, so
-//   * the count is read from DEVICE memory (ptr[8]: const int64*, incremented on the device by the caller), and
-//   * the bias corrections C1 = 1/(1-b1^count), C2 = 1/(1-b2^count) come from device TABLES (ptr[9], ptr[10]) indexed by
-//     count.  The tables are filled on the host with the very expressions the other launchers use (std::pow in double,
-//     one rounding to CT), so results stay bit-identical to the host-scalar path; they end where both corrections have
-//     become exactly 1 in CT (count 16 628 for b2 = 0.999 in fp32), and larger counts clamp to the last entry.
-// `flags` of the table carries the table length.
-template <typename TG_, typename TS_, typename CT_>
-struct StepFwdCap : StepFwd<TG_, TS_, CT_, true> {
-  using Base = StepFwd<TG_, TS_, CT_, true>;
-  using CT = CT_;
-  using Leaf = typename Base::Leaf;
-  static constexpr int NPTR = 11;
-  template <class Tab>
-  static __device__ __forceinline__ Leaf leaf(const Tab &t, int l) {
-    Leaf L = Base::leaf(t, l);
-    const long long c = *(const long long *)t.ptr[8][l];
-    const int len = t.flags;
-    const int idx = c < 1 ? 0 : (c > (long long)len ? len - 1 : (int)c - 1);
-    L.C1 = ((const CT *)t.ptr[9][l])[idx];
-    L.C2 = ((const CT *)t.ptr[10][l])[idx];
-    return L;
-  }
-};
-
 // backward of the whole step.  Incoming: dp' (gradient of the new parameters), dmu_ext, dnu_ext (gradients of the new
 // moments from later steps) and optionally dus (gradient of the returned scaled update, normally absent).
 //   du_s  = dp' (+ dus)            AddBackward of p' = p + us: both inputs receive dp'      (dp = dp' is returned by
@@ -554,8 +555,9 @@ struct StepBwd {
   using TG = TG_;
   using TS = TS_;
   using CT = CT_;
-  static constexpr int NPTR = 12, NGS = 10, NLS = 4;
-  static constexpr int MAXL_BIG = 160;  // 12 pointers + 4 scalars per leaf: 160 leaves keep the table under 32 KB
+  // ptr[12..16] (optional, NULL = host scalars): device step count + c1 / c2 / o1 / c2e tables (capturable form)
+  static constexpr int NPTR = 17, NGS = 10, NLS = 4;
+  static constexpr int MAXL_BIG = 160;  // 17 pointers + 4 scalars per leaf: 160 leaves keep the table under 32 KB
   struct Leaf {
     const TG *dp, *dus, *g, *p;
     const TS *m, *v, *dmu_ext, *dnu_ext;
@@ -573,7 +575,13 @@ struct StepBwd {
     L.p = (const TG *)t.ptr[10][l], L.dp_o = (TG *)t.ptr[11][l];
     L.B1 = t.gs[0], L.OMB1 = t.gs[1], L.B2 = t.gs[2], L.TWO_OMB2 = t.gs[3], L.ER = t.gs[4], L.EPS = t.gs[5];
     L.S = t.gs[6], L.WD1 = t.gs[7], L.WD2 = t.gs[8], L.SGN = t.gs[9];
-    L.O1 = t.ls[0][l], L.C2E = t.ls[1][l], L.C1 = t.ls[2][l], L.C2 = t.ls[3][l];
+    if (t.ptr[12][l] != nullptr) {
+      const int idx = bias_index(t.ptr[12][l], t.flags);
+      L.C1 = ((const CT *)t.ptr[13][l])[idx], L.C2 = ((const CT *)t.ptr[14][l])[idx];
+      L.O1 = ((const CT *)t.ptr[15][l])[idx], L.C2E = ((const CT *)t.ptr[16][l])[idx];
+    } else {
+      L.O1 = t.ls[0][l], L.C2E = t.ls[1][l], L.C1 = t.ls[2][l], L.C2 = t.ls[3][l];
+    }
     return L;
   }
   // raw p is read only when the effective gradient g2 = fma(WD1, p, +-g) has to be re-derived for backward_nu

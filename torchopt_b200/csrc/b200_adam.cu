@@ -118,6 +118,7 @@ static int pick_chunk_elems(long long total_elems, int sms) {
 
 template <class Op, int P, int U, int BLOCK, int MAXL>
 static int launch_table(Table<Op, MAXL> &tab, const DeviceInfo &di, cudaStream_t stream) {
+  static_assert(sizeof(Table<Op, MAXL>) <= 32764, "the leaf table must fit the 32 KB kernel-parameter space of sm_100");
   if (tab.total_chunks <= 0) return 0;
   // default: one CTA per chunk (non-persistent).  ctas_per_sm > 0 selects a persistent grid of that many CTAs/SM.
   const int per_sm = g_ctas_per_sm.load(std::memory_order_relaxed);
@@ -153,7 +154,7 @@ static int run_batches(long long num_leaves, long long total_elems, int flags, c
   };
   reset();
   for (long long i = 0; i < num_leaves; ++i) {
-    HostLeaf<Op> hl;
+    HostLeaf<Op> hl{};  // optional pointers (capturable count / tables) default to NULL
     if (!next(i, hl)) continue;
     long long off = 0;
     // a leaf with more than INT_MAX/2 chunks is split into several table entries (keeps chunk ids in int)
@@ -200,6 +201,32 @@ static int run_op(long long num_leaves, long long total_elems, int flags, const 
   if (num_leaves <= 1) return run_batches<Op, P, U, BLOCK, 1>(num_leaves, total_elems, flags, gs, next, stream);
   if (num_leaves <= 64) return run_batches<Op, P, U, BLOCK, 64>(num_leaves, total_elems, flags, gs, next, stream);
   return run_batches<Op, P, U, BLOCK, max_leaves<Op>()>(num_leaves, total_elems, flags, gs, next, stream);
+}
+
+// ---- size-dependent launch shape (profiles/r02_tune_mid.md) ------------------------------------------
+// The shapes tuned at 2^28 elements (r01_tune_sweep.md) are not the best for mid-size launches, where a launch is only
+// 3-30 waves of CTAs and the last, partially filled wave is a visible share of it:
+//   * forward: below 2^23 elements 256-thread CTAs (finer last wave) beat 512-thread CTAs by 12 % at 2^22 and tie above;
+//   * backward: the U=2 shape (two vectors in flight per array per thread, 8192 elements per CTA, one CTA per SM) loses
+//     20 % at 2^22 and 3 % at 2^24 against U=1 and only pays off (+0-1 %) from 2^26 on.
+constexpr long long kFwdSmallBlockBelow = 1ll << 23;
+constexpr long long kBwdSingleVectorBelow = 1ll << 26;
+
+template <class Op, int P, int U, class NextFn>
+static int run_fwd_sized(long long num_leaves, long long total, int flags, const typename Op::CT *gs, NextFn &&next,
+                         cudaStream_t stream) {
+  if (B200_ADAM_BLOCK > 256 && total < kFwdSmallBlockBelow)
+    return run_op<Op, P, U, 256>(num_leaves, total, flags, gs, next, stream);
+  return run_op<Op, P, U>(num_leaves, total, flags, gs, next, stream);
+}
+
+template <class Op, int P, int U, class NextFn>
+static int run_bwd_sized(long long num_leaves, long long total, int flags, const typename Op::CT *gs, NextFn &&next,
+                         cudaStream_t stream) {
+  if constexpr (U > 1) {
+    if (total < kBwdSingleVectorBelow) return run_op<Op, P, 1>(num_leaves, total, flags, gs, next, stream);
+  }
+  return run_op<Op, P, U>(num_leaves, total, flags, gs, next, stream);
 }
 
 // ---- host wrappers that give every Op an `advance` (pointer bump for >2^28-chunk leaves) ------------
@@ -266,7 +293,7 @@ static int fused_forward_impl(int64_t L, const void *const *g, const void *const
     return true;
   };
   using C = Cfg<TG, TS>;
-  return run_op<Op, C::P_FWD, C::U_FWD>(L, total, 0, gs, next, stream);
+  return run_fwd_sized<Op, C::P_FWD, C::U_FWD>(L, total, 0, gs, next, stream);
 }
 
 template <bool INPLACE>
@@ -326,7 +353,7 @@ static int fused_backward_mode(int64_t L, const void *const *du, const void *con
     // run-time presence flags cost registers: half-width vectors, no unroll, 128-thread CTAs (spill-free)
     return run_op<Op, C::P_BWD / 2, 1, 128>(L, total, 0, gs, next, stream);
   } else {
-    return run_op<Op, C::P_BWD, C::U_BWD>(L, total, 0, gs, next, stream);
+    return run_bwd_sized<Op, C::P_BWD, C::U_BWD>(L, total, 0, gs, next, stream);
   }
 }
 
@@ -368,14 +395,6 @@ struct StepFwdH : StepFwd<TG, TS, CT, INPLACE> {
       if (p[a]) p[a] = (char *)p[a] + (size_t)k * sz[a];
   }
 };
-template <typename TG, typename TS, typename CT>
-struct StepFwdCapH : StepFwdCap<TG, TS, CT> {
-  static void advance(void **p, long long k) {  // the count pointer and the two tables (8..10) do not move
-    const size_t sz[8] = {sizeof(TG), sizeof(TG), sizeof(TS), sizeof(TS), sizeof(TG), sizeof(TS), sizeof(TS), sizeof(TG)};
-    for (int a = 0; a < 8; ++a)
-      if (p[a]) p[a] = (char *)p[a] + (size_t)k * sz[a];
-  }
-};
 template <typename TG, typename TS, typename CT, int MODE>
 struct StepBwdH : StepBwd<TG, TS, CT, MODE> {
   static void advance(void **p, long long k) {
@@ -386,12 +405,20 @@ struct StepBwdH : StepBwd<TG, TS, CT, MODE> {
   }
 };
 
+// Capturable launches: per-leaf DEVICE step counts + device bias tables instead of host counts (count == NULL then).
+struct DeviceCounts {
+  const int64_t *const *count_dev = nullptr;
+  const void *c1 = nullptr, *c2 = nullptr, *o1 = nullptr, *c2e = nullptr;
+  int64_t len = 0;
+  bool on() const { return count_dev != nullptr; }
+};
+
 template <typename TG, typename TS, typename T, bool INPLACE>
 static int step_forward_impl(int64_t L, const void *const *p, const void *const *g, const void *const *mu,
                              const void *const *nu, void *const *p_out, void *const *mu_out, void *const *nu_out,
                              void *const *us_out, const int64_t *n, const uint64_t *count, double b1, double b2,
                              double eps, double eps_root, double step_size, double wd_l2, double wd_decoupled,
-                             int maximize, cudaStream_t stream) {
+                             int maximize, cudaStream_t stream, const DeviceCounts &dc = DeviceCounts()) {
   using Op = StepFwdH<TG, TS, T, INPLACE>;
   const T B1 = (T)b1, B2 = (T)b2;
   const T gs[10] = {B1, T(1) - B1, B2, T(1) - B2, (T)eps_root, (T)eps, (T)step_size, (T)wd_l2, (T)wd_decoupled,
@@ -401,13 +428,17 @@ static int step_forward_impl(int64_t L, const void *const *p, const void *const 
     if (n[i] < 0) return B200_ADAM_E_ARG;
     if (n[i] > 0 && (!p[i] || !g[i] || !mu[i] || !nu[i] || !p_out[i] || !mu_out[i] || !nu_out[i]))
       return B200_ADAM_E_ARG;
+    if (n[i] > 0 && dc.on() && !dc.count_dev[i]) return B200_ADAM_E_ARG;
     total += n[i];
   }
   uint64_t last_count = ~0ull;
   T c1 = 0, c2 = 0;
   auto next = [&](long long i, HostLeaf<Op> &hl) {
     if (n[i] == 0) return false;
-    if (count[i] != last_count) {
+    if (dc.on()) {  // corrections come from the device tables, indexed by the device count
+      hl.ptr[8] = const_cast<int64_t *>(dc.count_dev[i]);
+      hl.ptr[9] = const_cast<void *>(dc.c1), hl.ptr[10] = const_cast<void *>(dc.c2);
+    } else if (count[i] != last_count) {
       last_count = count[i];
       c1 = (T)inv_one_minus_pow(b1, last_count);
       c2 = (T)inv_one_minus_pow(b2, last_count);
@@ -420,7 +451,7 @@ static int step_forward_impl(int64_t L, const void *const *p, const void *const 
     return true;
   };
   using C = Cfg<TG, TS>;
-  return run_op<Op, C::P_FWD, C::U_FWD>(L, total, 0, gs, next, stream);
+  return run_fwd_sized<Op, C::P_FWD, C::U_FWD>(L, total, (int)dc.len, gs, next, stream);
 }
 
 template <typename TG, typename TS, typename T>
@@ -429,28 +460,10 @@ static int step_capturable_impl(int64_t L, void *const *p, void *const *g, void 
                                 const void *c2_table, int64_t table_len, double b1, double b2, double eps,
                                 double eps_root, double step_size, double wd_l2, double wd_decoupled, int maximize,
                                 int overwrite_grads, cudaStream_t stream) {
-  using Op = StepFwdCapH<TG, TS, T>;
-  const T B1 = (T)b1, B2 = (T)b2;
-  const T gs[10] = {B1, T(1) - B1, B2, T(1) - B2, (T)eps_root, (T)eps, (T)step_size, (T)wd_l2, (T)wd_decoupled,
-                    maximize ? T(-1) : T(1)};
-  long long total = 0;
-  for (int64_t i = 0; i < L; ++i) {
-    if (n[i] < 0) return B200_ADAM_E_ARG;
-    if (n[i] > 0 && (!p[i] || !g[i] || !mu[i] || !nu[i] || !count_dev[i])) return B200_ADAM_E_ARG;
-    total += n[i];
-  }
-  auto next = [&](long long i, HostLeaf<Op> &hl) {
-    if (n[i] == 0) return false;
-    hl.ptr[0] = p[i], hl.ptr[1] = g[i], hl.ptr[2] = mu[i], hl.ptr[3] = nu[i];
-    hl.ptr[4] = p[i], hl.ptr[5] = mu[i], hl.ptr[6] = nu[i], hl.ptr[7] = overwrite_grads ? g[i] : nullptr;
-    hl.ptr[8] = const_cast<int64_t *>(count_dev[i]);
-    hl.ptr[9] = const_cast<void *>(c1_table), hl.ptr[10] = const_cast<void *>(c2_table);
-    hl.n = n[i];
-    hl.ls[0] = T(0), hl.ls[1] = T(0);  // unused: the corrections come from the device tables
-    return true;
-  };
-  using C = Cfg<TG, TS>;
-  return run_op<Op, C::P_FWD, C::U_FWD>(L, total, (int)table_len, gs, next, stream);
+  DeviceCounts dc;
+  dc.count_dev = count_dev, dc.c1 = c1_table, dc.c2 = c2_table, dc.len = table_len;
+  return step_forward_impl<TG, TS, T, true>(L, p, g, mu, nu, p, mu, nu, overwrite_grads ? g : nullptr, n, nullptr, b1, b2,
+                                            eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, stream, dc);
 }
 
 // number of table entries after which 1/(1-b^count) is exactly 1 in T for every larger count (the value decreases
@@ -467,13 +480,53 @@ static int64_t bias_table_len_one(double b, int64_t cap) {
   return lo;
 }
 
+// smallest count from which `value(c)` equals `limit` (value is monotone in c and converges to limit); 0 if that does
+// not happen within `cap` counts
+template <class F>
+static int64_t first_count_at_limit(F &&at_limit, int64_t cap) {
+  if (!at_limit(cap)) return 0;
+  int64_t lo = 1, hi = cap;
+  while (lo < hi) {
+    const int64_t mid = lo + (hi - lo) / 2;
+    if (at_limit(mid)) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// length of the FOUR bias tables (c1, c2 for the forward; o1, c2e in addition for the backward): the count from which
+// every correction has reached its limit value in T
+template <typename T>
+static int64_t bias_table_len_all(double b1, double b2, double eps_root, int64_t cap) {
+  const T c2e_limit = (T)(1 / (1 - 0.0 + eps_root));
+  const int64_t a = first_count_at_limit([&](int64_t c) { return (T)inv_one_minus_pow(b1, (uint64_t)c) == T(1); }, cap);
+  const int64_t b = first_count_at_limit([&](int64_t c) { return (T)inv_one_minus_pow(b2, (uint64_t)c) == T(1); }, cap);
+  const int64_t d = first_count_at_limit([&](int64_t c) { return (T)one_minus_pow(b1, (uint64_t)c) == T(1); }, cap);
+  const int64_t e = first_count_at_limit(
+      [&](int64_t c) { return (T)inv_one_minus_pow_eps(b2, eps_root, (uint64_t)c) == c2e_limit; }, cap);
+  if (a == 0 || b == 0 || d == 0 || e == 0) return 0;
+  int64_t m = a > b ? a : b;
+  m = d > m ? d : m;
+  return e > m ? e : m;
+}
+
+template <typename T>
+static void fill_bias_tables(double b1, double b2, double eps_root, int64_t len, void *c1, void *c2, void *o1, void *c2e) {
+  for (int64_t c = 1; c <= len; ++c) {
+    ((T *)c1)[c - 1] = (T)inv_one_minus_pow(b1, (uint64_t)c);
+    ((T *)c2)[c - 1] = (T)inv_one_minus_pow(b2, (uint64_t)c);
+    if (o1) ((T *)o1)[c - 1] = (T)one_minus_pow(b1, (uint64_t)c);
+    if (c2e) ((T *)c2e)[c - 1] = (T)inv_one_minus_pow_eps(b2, eps_root, (uint64_t)c);
+  }
+}
+
 template <typename TG, typename TS, typename T, int MODE>
 static int step_backward_mode(int64_t L, const void *const *dp, const void *const *dus, const void *const *new_mu,
                               const void *const *new_nu, const void *const *g, const void *const *dmu_ext,
                               const void *const *dnu_ext, void *const *dg, void *const *dmu, void *const *dnu,
                               const void *const *p, void *const *dp_out, const int64_t *n, const uint64_t *count,
                               double b1, double b2, double eps, double eps_root, double step_size, double wd_l2,
-                              double wd_decoupled, int maximize, long long total, cudaStream_t stream) {
+                              double wd_decoupled, int maximize, long long total, cudaStream_t stream,
+                              const DeviceCounts &dc) {
   using Op = StepBwdH<TG, TS, T, MODE>;
   const T B1 = (T)b1, B2 = (T)b2;
   const T gs[10] = {B1, T(1) - B1, B2, T(2) * (T(1) - B2), (T)eps_root, (T)eps, (T)step_size, (T)wd_l2,
@@ -484,7 +537,11 @@ static int step_backward_mode(int64_t L, const void *const *dp, const void *cons
     if (n[i] == 0) return false;
     void *dpo = dp_out ? dp_out[i] : nullptr;
     if (!dg[i] && !dmu[i] && !dnu[i] && !dpo) return false;
-    if (count[i] != last_count) {
+    if (dc.on()) {
+      hl.ptr[12] = const_cast<int64_t *>(dc.count_dev[i]);
+      hl.ptr[13] = const_cast<void *>(dc.c1), hl.ptr[14] = const_cast<void *>(dc.c2);
+      hl.ptr[15] = const_cast<void *>(dc.o1), hl.ptr[16] = const_cast<void *>(dc.c2e);
+    } else if (count[i] != last_count) {
       last_count = count[i];
       o1 = (T)one_minus_pow(b1, last_count);
       c2e = (T)inv_one_minus_pow_eps(b2, eps_root, last_count);
@@ -500,13 +557,13 @@ static int step_backward_mode(int64_t L, const void *const *dp, const void *cons
   };
   using C = Cfg<TG, TS>;
   if constexpr (MODE == BWD_GENERIC) {
-    return run_op<Op, C::P_BWD / 2, 1, 128>(L, total, 0, gs, next, stream);
+    return run_op<Op, C::P_BWD / 2, 1, 128>(L, total, (int)dc.len, gs, next, stream);
   } else {
     // The step backward recomputes u (one more IEEE div + sqrt) and carries one more stream (p) than FusedBwd, so it
     // is the most instruction-heavy kernel of the family.  Measured (profiles/r01_tune_step.md): U=2 needs 142
     // registers and halves the resident warps (4.4-4.6 TB/s); U=1 with SMALL CTAs is best -- 128 threads x 92
     // registers = 5 CTAs (20 warps) per SM, whose compute phases interleave with each other's loads: 7.13 TB/s.
-    return run_op<Op, C::P_BWD, B200_STEP_U_BWD, B200_STEP_BLOCK_BWD>(L, total, 0, gs, next, stream);
+    return run_op<Op, C::P_BWD, B200_STEP_U_BWD, B200_STEP_BLOCK_BWD>(L, total, (int)dc.len, gs, next, stream);
   }
 }
 
@@ -516,13 +573,15 @@ static int step_backward_impl(int64_t L, const void *const *dp, const void *cons
                               const void *const *dnu_ext, void *const *dg, void *const *dmu, void *const *dnu,
                               const void *const *p, void *const *dp_out, const int64_t *n, const uint64_t *count,
                               double b1, double b2, double eps, double eps_root, double step_size, double wd_l2,
-                              double wd_decoupled, int maximize, cudaStream_t stream) {
+                              double wd_decoupled, int maximize, cudaStream_t stream,
+                              const DeviceCounts &dc = DeviceCounts()) {
   bool all_full = true, all_last = true;
   long long total = 0;
   for (int64_t i = 0; i < L; ++i) {
     if (n[i] < 0) return B200_ADAM_E_ARG;
     if (n[i] == 0) continue;
     total += n[i];
+    if (dc.on() && !dc.count_dev[i]) return B200_ADAM_E_ARG;
     const bool hdp = dp[i] != nullptr, hdus = dus && dus[i] != nullptr;
     const bool hme = dmu_ext[i] != nullptr, hne = dnu_ext[i] != nullptr;
     if ((hdp || hdus) && (!new_mu[i] || !new_nu[i])) return B200_ADAM_E_ARG;
@@ -536,7 +595,7 @@ static int step_backward_impl(int64_t L, const void *const *dp, const void *cons
   if (total == 0) return 0;
 #define B200_STEP_BWD(MODE)                                                                                      \
   step_backward_mode<TG, TS, T, MODE>(L, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, p, dp_out, n, count, b1, \
-                              b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, total, stream)
+                              b2, eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, total, stream, dc)
   if (all_full) return B200_STEP_BWD(BWD_FULL);
   if (all_last) return B200_STEP_BWD(BWD_LAST);
   return B200_STEP_BWD(BWD_GENERIC);
@@ -629,35 +688,30 @@ int b200_adam_query_launch(int dtype, int backward, int64_t n, int32_t out[5]) {
   if (!out || n < 0) return B200_ADAM_E_ARG;
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
-  constexpr int BLOCK = B200_ADAM_BLOCK;
-  int P, U, occ, chunk;
-#define B200_Q(TG, TS, CT)                                                                                    \
-  if (backward) {                                                                                             \
-    using Op = BwdH<TG, TS, CT, BWD_FULL>;                                                                    \
-    P = Cfg<TG, TS>::P_BWD, U = Cfg<TG, TS>::U_BWD;                                                           \
-    occ = occupancy_ctas_per_sm<Op, Cfg<TG, TS>::P_BWD, Cfg<TG, TS>::U_BWD, BLOCK, 1>();                      \
-    chunk = pick_chunk_elems<Op, Cfg<TG, TS>::P_BWD, Cfg<TG, TS>::U_BWD, BLOCK>(n, di.sms);                   \
-  } else {                                                                                                    \
-    using Op = FwdH<TG, TS, CT, false>;                                                                       \
-    P = Cfg<TG, TS>::P_FWD, U = Cfg<TG, TS>::U_FWD;                                                           \
-    occ = occupancy_ctas_per_sm<Op, Cfg<TG, TS>::P_FWD, Cfg<TG, TS>::U_FWD, BLOCK, 1>();                      \
-    chunk = pick_chunk_elems<Op, Cfg<TG, TS>::P_FWD, Cfg<TG, TS>::U_FWD, BLOCK>(n, di.sms);                   \
-  }
+  int block = B200_ADAM_BLOCK, P, U;
   switch (dtype) {
-    case B200_ADAM_F32: B200_Q(float, float, float) break;
+    case B200_ADAM_F32: P = backward ? Cfg<float, float>::P_BWD : Cfg<float, float>::P_FWD,
+                        U = backward ? Cfg<float, float>::U_BWD : Cfg<float, float>::U_FWD; break;
 #ifndef B200_ADAM_TUNE_F32_ONLY
-    case B200_ADAM_F64: B200_Q(double, double, double) break;
-    case B200_ADAM_BF16_F32: B200_Q(bf16_t, float, float) break;
+    case B200_ADAM_F64: P = backward ? Cfg<double, double>::P_BWD : Cfg<double, double>::P_FWD,
+                        U = backward ? Cfg<double, double>::U_BWD : Cfg<double, double>::U_FWD; break;
+    case B200_ADAM_BF16_F32: P = backward ? Cfg<bf16_t, float>::P_BWD : Cfg<bf16_t, float>::P_FWD,
+                             U = backward ? Cfg<bf16_t, float>::U_BWD : Cfg<bf16_t, float>::U_FWD; break;
 #endif
     default: return B200_ADAM_E_DTYPE;
   }
-#undef B200_Q
+  // the size-dependent shape of run_fwd_sized / run_bwd_sized
+  if (!backward && block > 256 && n < kFwdSmallBlockBelow) block = 256;
+  if (backward && U > 1 && n < kBwdSingleVectorBelow) U = 1;
+  int tiles = g_tiles_per_chunk.load(std::memory_order_relaxed);
+  const long long tile = (long long)block * P * U;
+  if (tiles <= 0 || n < tile * tiles * di.sms * 4) tiles = 1;
+  const int chunk = (int)(tile * tiles);
   const int per_sm = g_ctas_per_sm.load();
   const long long chunks = (n + chunk - 1) / chunk;
   long long grid = chunks;
   if (per_sm > 0 && (long long)di.sms * per_sm < grid) grid = (long long)di.sms * per_sm;
-  (void)occ;  // occupancy is informational only since the default grid is non-persistent
-  out[0] = (int32_t)grid, out[1] = BLOCK, out[2] = chunk, out[3] = P, out[4] = U;
+  out[0] = (int32_t)grid, out[1] = block, out[2] = chunk, out[3] = P, out[4] = U;
   return 0;
 }
 
@@ -878,6 +932,85 @@ int b200_adam_step_backward(int dtype, int64_t num_leaves, const void *const *dp
 #endif
   if (dtype == B200_ADAM_F32) B200_STEP_BWD_DT(float, float, float);
 #undef B200_STEP_BWD_DT
+  return B200_ADAM_E_DTYPE;
+}
+
+int64_t b200_adam_bias_table_len_ex(int dtype, double b1, double b2, double eps_root) {
+  if (!(b1 >= 0.0 && b1 < 1.0 && b2 >= 0.0 && b2 < 1.0) || !(eps_root >= 0.0)) return B200_ADAM_E_ARG;
+  const int64_t cap = int64_t(1) << 24;
+  int64_t len;
+  if (dtype == B200_ADAM_F64) len = bias_table_len_all<double>(b1, b2, eps_root, cap);
+  else if (dtype == B200_ADAM_F32 || dtype == B200_ADAM_BF16_F32) len = bias_table_len_all<float>(b1, b2, eps_root, cap);
+  else return B200_ADAM_E_DTYPE;
+  return len == 0 ? (int64_t)B200_ADAM_E_ARG : len;
+}
+
+int b200_adam_bias_table_ex(int dtype, double b1, double b2, double eps_root, int64_t len, void *c1_host, void *c2_host,
+                            void *o1_host, void *c2e_host) {
+  if (len <= 0 || !c1_host || !c2_host || !o1_host || !c2e_host) return B200_ADAM_E_ARG;
+  if (dtype == B200_ADAM_F64) fill_bias_tables<double>(b1, b2, eps_root, len, c1_host, c2_host, o1_host, c2e_host);
+  else if (dtype == B200_ADAM_F32 || dtype == B200_ADAM_BF16_F32)
+    fill_bias_tables<float>(b1, b2, eps_root, len, c1_host, c2_host, o1_host, c2e_host);
+  else return B200_ADAM_E_DTYPE;
+  return 0;
+}
+
+int b200_adam_step_forward_capturable(int dtype, int64_t num_leaves, const void *const *p, const void *const *g,
+                                      const void *const *mu, const void *const *nu, void *const *p_out,
+                                      void *const *mu_out, void *const *nu_out, void *const *us_out, const int64_t *n,
+                                      const int64_t *const *count_dev, const void *c1_table_dev, const void *c2_table_dev,
+                                      int64_t table_len, double b1, double b2, double eps, double eps_root,
+                                      double step_size, double wd_l2, double wd_decoupled, int maximize, void *stream) {
+  if (num_leaves < 0) return B200_ADAM_E_ARG;
+  if (num_leaves == 0) return 0;
+  if (!p || !g || !mu || !nu || !p_out || !mu_out || !nu_out || !n || !count_dev || !c1_table_dev || !c2_table_dev ||
+      table_len <= 0 || table_len > (int64_t(1) << 24))
+    return B200_ADAM_E_ARG;
+  if (wd_l2 != 0.0 && wd_decoupled != 0.0) return B200_ADAM_E_ARG;
+  DeviceCounts dc;
+  dc.count_dev = count_dev, dc.c1 = c1_table_dev, dc.c2 = c2_table_dev, dc.len = table_len;
+  cudaStream_t s = (cudaStream_t)stream;
+#define B200_STEP_FWD_CAP(TG, TS, CT)                                                                                 \
+  return step_forward_impl<TG, TS, CT, false>(num_leaves, p, g, mu, nu, p_out, mu_out, nu_out, us_out, n, nullptr, b1, b2, \
+                                              eps, eps_root, step_size, wd_l2, wd_decoupled, maximize, s, dc)
+#ifndef B200_ADAM_TUNE_F32_ONLY
+  if (dtype == B200_ADAM_F64) B200_STEP_FWD_CAP(double, double, double);
+  if (dtype == B200_ADAM_BF16_F32) B200_STEP_FWD_CAP(bf16_t, float, float);
+#endif
+  if (dtype == B200_ADAM_F32) B200_STEP_FWD_CAP(float, float, float);
+#undef B200_STEP_FWD_CAP
+  return B200_ADAM_E_DTYPE;
+}
+
+int b200_adam_step_backward_capturable(int dtype, int64_t num_leaves, const void *const *dp, const void *const *dus,
+                                       const void *const *new_mu, const void *const *new_nu, const void *const *g,
+                                       const void *const *dmu_ext, const void *const *dnu_ext, void *const *dg,
+                                       void *const *dmu, void *const *dnu, const void *const *p, void *const *dp_out,
+                                       const int64_t *n, const int64_t *const *count_dev, const void *c1_table_dev,
+                                       const void *c2_table_dev, const void *o1_table_dev, const void *c2e_table_dev,
+                                       int64_t table_len, double b1, double b2, double eps, double eps_root,
+                                       double step_size, double wd_l2, double wd_decoupled, int maximize, void *stream) {
+  if (num_leaves < 0) return B200_ADAM_E_ARG;
+  if (num_leaves == 0) return 0;
+  if (!dp || !new_mu || !new_nu || !g || !dmu_ext || !dnu_ext || !dg || !dmu || !dnu || !n || !count_dev ||
+      !c1_table_dev || !c2_table_dev || !o1_table_dev || !c2e_table_dev || table_len <= 0 ||
+      table_len > (int64_t(1) << 24))
+    return B200_ADAM_E_ARG;
+  if (wd_l2 != 0.0 && wd_decoupled != 0.0) return B200_ADAM_E_ARG;
+  DeviceCounts dc;
+  dc.count_dev = count_dev, dc.c1 = c1_table_dev, dc.c2 = c2_table_dev, dc.o1 = o1_table_dev, dc.c2e = c2e_table_dev;
+  dc.len = table_len;
+  cudaStream_t s = (cudaStream_t)stream;
+#define B200_STEP_BWD_CAP(TG, TS, CT)                                                                                  \
+  return step_backward_impl<TG, TS, CT>(num_leaves, dp, dus, new_mu, new_nu, g, dmu_ext, dnu_ext, dg, dmu, dnu, p,       \
+                                        dp_out, n, nullptr, b1, b2, eps, eps_root, step_size, wd_l2, wd_decoupled,       \
+                                        maximize, s, dc)
+#ifndef B200_ADAM_TUNE_F32_ONLY
+  if (dtype == B200_ADAM_F64) B200_STEP_BWD_CAP(double, double, double);
+  if (dtype == B200_ADAM_BF16_F32) B200_STEP_BWD_CAP(bf16_t, float, float);
+#endif
+  if (dtype == B200_ADAM_F32) B200_STEP_BWD_CAP(float, float, float);
+#undef B200_STEP_BWD_CAP
   return B200_ADAM_E_DTYPE;
 }
 

@@ -792,11 +792,41 @@ inline void copy_ranges(Tensor &dst, const Tensor &src, const std::vector<int64_
 }
 
 // forward without autograd: returns p'_0.., mu'_flat, nu'_flat ; `cp`, `cg` receive the row-major tensors actually read
+// Capturable form: `tensors` carries five more entries -- the per-leaf device step counts of THIS step (an int64 vector,
+// entry cidx[k] belongs to live leaf k; already incremented, snapshotted by the caller) and the four bias tables
+// c1, c2, o1, c2e -- and `cidx` is non-empty; the host `counts` are then ignored.
+struct CapTensors {
+  const Tensor *cnt = nullptr, *c1 = nullptr, *c2 = nullptr, *o1 = nullptr, *c2e = nullptr;
+  bool on() const { return cnt != nullptr; }
+  void check(int dt, const Tensor &mu_flat) const {
+    const auto table_type = dt == B200_ADAM_F64 ? at::kDouble : at::kFloat;
+    for (const Tensor *t : {c1, c2, o1, c2e})
+      if (!t->is_cuda() || t->scalar_type() != table_type || !t->is_contiguous() || t->numel() != c1->numel() ||
+          t->numel() == 0 || t->device() != mu_flat.device())
+        throw std::runtime_error("flat_step: bias tables must be contiguous CUDA tensors of the arithmetic type");
+    if (!cnt->is_cuda() || cnt->scalar_type() != at::kLong || !cnt->is_contiguous() || cnt->device() != mu_flat.device())
+      throw std::runtime_error("flat_step: the device step counts must be a contiguous int64 CUDA vector");
+  }
+};
+
+inline CapTensors cap_tensors(at::TensorList tensors, size_t K, const std::vector<int64_t> &cidx) {
+  CapTensors c;
+  if (cidx.empty()) return c;
+  if (tensors.size() != 2 * K + 7 || cidx.size() != K)
+    throw std::runtime_error("flat_step: the capturable form expects count vector + 4 bias tables after the flat moments");
+  c.cnt = &tensors[2 * K + 2], c.c1 = &tensors[2 * K + 3], c.c2 = &tensors[2 * K + 4];
+  c.o1 = &tensors[2 * K + 5], c.c2e = &tensors[2 * K + 6];
+  for (int64_t i : cidx)
+    if (i < 0 || i >= c.cnt->numel()) throw std::runtime_error("flat_step: step-count index out of range");
+  return c;
+}
+
 variable_list flat_step_forward(at::TensorList tensors, const std::vector<int64_t> &offs, const std::vector<int64_t> &keep,
                                 const std::vector<int64_t> &counts, const std::vector<double> &hyper,
-                                std::vector<Tensor> &cp, std::vector<Tensor> &cg) {
+                                std::vector<Tensor> &cp, std::vector<Tensor> &cg, const std::vector<int64_t> &cidx) {
   const size_t K = counts.size();
-  if (tensors.size() != 2 * K + 2 || offs.size() != K || hyper.size() != 8)
+  const CapTensors cap = cap_tensors(tensors, K, cidx);
+  if ((!cap.on() && tensors.size() != 2 * K + 2) || offs.size() != K || hyper.size() != 8)
     throw std::runtime_error("flat_step: expected p_0.., g_0.., mu_flat, nu_flat with one offset and count per leaf");
   const Tensor &mu_flat = tensors[2 * K], &nu_flat = tensors[2 * K + 1];
   if (mu_flat.dim() != 1 || !mu_flat.is_contiguous() || !nu_flat.is_contiguous() || mu_flat.sizes() != nu_flat.sizes())
@@ -832,10 +862,22 @@ variable_list flat_step_forward(at::TensorList tensors, const std::vector<int64_
       q.po[k] = fa[k].data_ptr(), q.muo[k] = at_offset(mu_out, offs[k]), q.nuo[k] = at_offset(nu_out, offs[k]);
       q.n[k] = cp[k].numel(), q.cnt[k] = (uint64_t)counts[k];
     }
-    check(b200_adam_step_forward(dt, (int64_t)K, q.p.data(), q.g.data(), q.mu.data(), q.nu.data(), q.po.data(),
-                                 q.muo.data(), q.nuo.data(), nullptr, q.n.data(), q.cnt.data(), hyper[0], hyper[1],
-                                 hyper[2], hyper[3], hyper[4], hyper[5], hyper[6], hyper[7] != 0.0 ? 1 : 0, c.stream),
-          "flat_step");
+    if (cap.on()) {
+      cap.check(dt, mu_flat);
+      std::vector<const int64_t *> pc(K);
+      for (size_t k = 0; k < K; ++k) pc[k] = cap.cnt->data_ptr<int64_t>() + cidx[k];
+      check(b200_adam_step_forward_capturable(dt, (int64_t)K, q.p.data(), q.g.data(), q.mu.data(), q.nu.data(),
+                                              q.po.data(), q.muo.data(), q.nuo.data(), nullptr, q.n.data(), pc.data(),
+                                              cap.c1->data_ptr(), cap.c2->data_ptr(), cap.c1->numel(), hyper[0], hyper[1],
+                                              hyper[2], hyper[3], hyper[4], hyper[5], hyper[6], hyper[7] != 0.0 ? 1 : 0,
+                                              c.stream),
+            "flat_step (capturable)");
+    } else {
+      check(b200_adam_step_forward(dt, (int64_t)K, q.p.data(), q.g.data(), q.mu.data(), q.nu.data(), q.po.data(),
+                                   q.muo.data(), q.nuo.data(), nullptr, q.n.data(), q.cnt.data(), hyper[0], hyper[1],
+                                   hyper[2], hyper[3], hyper[4], hyper[5], hyper[6], hyper[7] != 0.0 ? 1 : 0, c.stream),
+            "flat_step");
+    }
   }
   result.push_back(mu_out), result.push_back(nu_out);
   return result;
@@ -843,13 +885,14 @@ variable_list flat_step_forward(at::TensorList tensors, const std::vector<int64_
 
 struct FlatStepNode : public torch::autograd::Function<FlatStepNode> {
   static variable_list forward(AutogradContext *ctx, at::TensorList tensors, std::vector<int64_t> offs,
-                               std::vector<int64_t> keep, std::vector<int64_t> counts, std::vector<double> hyper) {
+                               std::vector<int64_t> keep, std::vector<int64_t> counts, std::vector<double> hyper,
+                               std::vector<int64_t> cidx) {
     const size_t K = counts.size();
     std::vector<Tensor> cp, cg;
-    variable_list result = flat_step_forward(tensors, offs, keep, counts, hyper, cp, cg);
+    variable_list result = flat_step_forward(tensors, offs, keep, counts, hyper, cp, cg, cidx);
     ctx->set_materialize_grads(false);
     ctx->saved_data["offs"] = offs, ctx->saved_data["keep"] = keep;
-    ctx->saved_data["counts"] = counts, ctx->saved_data["hyper"] = hyper;
+    ctx->saved_data["counts"] = counts, ctx->saved_data["hyper"] = hyper, ctx->saved_data["cidx"] = cidx;
     variable_list saved;
     saved.reserve(2 * K + 2);
     saved.push_back(result[K]), saved.push_back(result[K + 1]);  // mu', nu' (u is recomputed in the backward kernel)
@@ -858,6 +901,8 @@ struct FlatStepNode : public torch::autograd::Function<FlatStepNode> {
     for (size_t k = 0; k < K; ++k) saved.push_back(cg[k]);
     if (hyper[5] != 0.0)
       for (size_t k = 0; k < K; ++k) saved.push_back(cp[k]);  // L2 decay: g2 = g + wd * p is re-derived
+    if (!cidx.empty())
+      for (size_t a = 0; a < 5; ++a) saved.push_back(tensors[2 * K + 2 + a]);  // count snapshot + the four tables
     ctx->save_for_backward(saved);
     return result;
   }
@@ -867,14 +912,16 @@ struct FlatStepNode : public torch::autograd::Function<FlatStepNode> {
     const auto keep = ctx->saved_data["keep"].toIntVector();
     const auto counts = ctx->saved_data["counts"].toIntVector();
     const auto hyper = ctx->saved_data["hyper"].toDoubleVector();
+    const auto cidx = ctx->saved_data["cidx"].toIntVector();
     const size_t K = counts.size();
-    const bool l2 = hyper[5] != 0.0, decay = l2 || hyper[6] != 0.0;
+    const bool l2 = hyper[5] != 0.0, decay = l2 || hyper[6] != 0.0, capt = !cidx.empty();
     const variable_list saved = ctx->get_saved_variables();
     const Tensor &new_mu = saved[0], &new_nu = saved[1];
+    const size_t n_in = 2 * K + 2 + (capt ? 5 : 0);   // tensor inputs of the forward
     Tensor dme = douts[K].defined() ? douts[K].contiguous() : Tensor();
     Tensor dne = douts[K + 1].defined() ? douts[K + 1].contiguous() : Tensor();
     const bool need_mu = ctx->needs_input_grad(2 * K), need_nu = ctx->needs_input_grad(2 * K + 1);
-    variable_list grads(2 * K + 6);  // dp_0.., dg_0.., dmu_flat, dnu_flat, then offs, keep, counts, hyper
+    variable_list grads(n_in + 5);  // dp_0.., dg_0.., dmu_flat, dnu_flat [, 5 capturable tensors], offs, keep, counts, hyper, cidx
     // a leaf that receives no gradient at all leaves its range of dmu / dnu unwritten by the kernel: start from zeros
     // whenever that can happen (some dp' missing, or skipped leaves), from uninitialised memory otherwise
     auto fully_written = [&](const Tensor &dext) {  // will the kernel write the range of EVERY leaf?
@@ -932,12 +979,27 @@ struct FlatStepNode : public torch::autograd::Function<FlatStepNode> {
       q.dpo[j] = slot_dp[k] >= 0 ? grads[k].data_ptr() : nullptr;
       q.n[j] = g.numel(), q.cnt[j] = (uint64_t)counts[k];
     }
-    if (G > 0)
+    if (G > 0 && capt) {
+      const size_t base = 2 + K + (l2 ? K : 0);
+      CapTensors cap;
+      cap.cnt = &saved[base], cap.c1 = &saved[base + 1], cap.c2 = &saved[base + 2], cap.o1 = &saved[base + 3];
+      cap.c2e = &saved[base + 4];
+      std::vector<const int64_t *> pc(G);
+      for (size_t j = 0; j < G; ++j) pc[j] = cap.cnt->data_ptr<int64_t>() + cidx[live[j]];
+      check(b200_adam_step_backward_capturable(dt, (int64_t)G, q.dp.data(), nullptr, q.mu.data(), q.nu.data(), q.g.data(),
+                                               q.dme.data(), q.dne.data(), q.dg.data(), q.dmu.data(), q.dnu.data(),
+                                               q.p.data(), q.dpo.data(), q.n.data(), pc.data(), cap.c1->data_ptr(),
+                                               cap.c2->data_ptr(), cap.o1->data_ptr(), cap.c2e->data_ptr(),
+                                               cap.c1->numel(), hyper[0], hyper[1], hyper[2], hyper[3], hyper[4], hyper[5],
+                                               hyper[6], hyper[7] != 0.0 ? 1 : 0, c.stream),
+            "flat_step backward (capturable)");
+    } else if (G > 0) {
       check(b200_adam_step_backward(dt, (int64_t)G, q.dp.data(), nullptr, q.mu.data(), q.nu.data(), q.g.data(),
                                     q.dme.data(), q.dne.data(), q.dg.data(), q.dmu.data(), q.dnu.data(), q.p.data(),
                                     q.dpo.data(), q.n.data(), q.cnt.data(), hyper[0], hyper[1], hyper[2], hyper[3], hyper[4],
                                     hyper[5], hyper[6], hyper[7] != 0.0 ? 1 : 0, c.stream),
             "flat_step backward");
+    }
     grads[2 * K] = dmu_flat, grads[2 * K + 1] = dnu_flat;
     return grads;
   }
@@ -954,10 +1016,15 @@ std::tuple<std::vector<Tensor>, Tensor, Tensor> flat_step(const std::vector<Tens
                                                           const std::vector<int64_t> &counts, double b1, double b2,
                                                           double eps, double eps_root, double step_size, double wd_l2,
                                                           double wd_decoupled, bool maximize, bool inplace,
-                                                          bool keep_grads) {
+                                                          bool keep_grads, const OptTensor &count_dev,
+                                                          const std::vector<Tensor> &tables) {
   const size_t L = params.size();
   if (grads.size() != L || offsets.size() != L || counts.size() != L)
     throw std::runtime_error("flat_step: params, grads, offsets and counts must have the same number of leaves");
+  const bool capt = count_dev.has_value();
+  if (capt && (tables.size() != 4 || inplace || count_dev->numel() != (int64_t)L))
+    throw std::runtime_error("flat_step: the capturable form takes one device count per leaf and the 4 bias tables "
+                             "(c1, c2, o1, c2e) and is out of place");
   std::vector<size_t> live;
   std::vector<int64_t> keep;
   for (size_t i = 0; i < L; ++i) {
@@ -999,12 +1066,17 @@ std::tuple<std::vector<Tensor>, Tensor, Tensor> flat_step(const std::vector<Tens
     return {new_p, mu_flat, nu_flat};
   }
   std::vector<Tensor> flat;
-  std::vector<int64_t> offs(K), cnt(K);
-  flat.reserve(2 * K + 2);
+  std::vector<int64_t> offs(K), cnt(K), cidx;
+  flat.reserve(2 * K + 7);
   for (size_t k = 0; k < K; ++k) flat.push_back(params[live[k]]), offs[k] = offsets[live[k]], cnt[k] = counts[live[k]];
   for (size_t k = 0; k < K; ++k) flat.push_back(*grads[live[k]]);
   flat.push_back(mu_flat), flat.push_back(nu_flat);
-  variable_list out = FlatStepNode::apply(at::TensorList(flat), offs, keep, cnt, hyper);
+  if (capt) {
+    flat.push_back(*count_dev);
+    for (const Tensor &t : tables) flat.push_back(t);
+    cidx.assign(live.begin(), live.end());
+  }
+  variable_list out = FlatStepNode::apply(at::TensorList(flat), offs, keep, cnt, hyper, cidx);
   for (size_t k = 0; k < K; ++k) new_p[live[k]] = out[k];
   return {new_p, out[K], out[K + 1]};
 }
@@ -1130,7 +1202,22 @@ PYBIND11_MODULE(_C, mod) {
         py::arg("params"), py::arg("updates"), py::arg("mu_flat"), py::arg("nu_flat"), py::arg("offsets"),
         py::arg("count"), py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("step_size"),
         py::arg("wd_l2") = 0.0, py::arg("wd_decoupled") = 0.0, py::arg("maximize") = false,
-        py::arg("inplace") = false, py::arg("keep_grads") = false);
+        py::arg("inplace") = false, py::arg("keep_grads") = false, py::arg("count_dev") = py::none(),
+        py::arg("tables") = std::vector<Tensor>());
+  m.def("bias_tables_ex",
+        [](int dtype_family, double b1, double b2, double eps_root) {
+          const int64_t len = b200_adam_bias_table_len_ex(dtype_family, b1, b2, eps_root);
+          if (len <= 0)
+            throw std::runtime_error("bias_tables_ex: betas this close to 1 need more than 2^24 table entries");
+          auto opts = at::TensorOptions().dtype(dtype_family == B200_ADAM_F64 ? at::kDouble : at::kFloat).device(at::kCPU);
+          std::vector<Tensor> t{at::empty({len}, opts), at::empty({len}, opts), at::empty({len}, opts), at::empty({len}, opts)};
+          check(b200_adam_bias_table_ex(dtype_family, b1, b2, eps_root, len, t[0].data_ptr(), t[1].data_ptr(),
+                                        t[2].data_ptr(), t[3].data_ptr()),
+                "bias_tables_ex");
+          return t;
+        },
+        "host-computed bias-correction tables [c1, c2, o1, c2e] for the capturable differentiable step",
+        py::arg("dtype_family"), py::arg("b1"), py::arg("b2"), py::arg("eps_root"));
   m.def("host_step", &host_step, "Fused forward+backward over pinned HOST tensors (pipelined H2D/compute/D2H)",
         py::arg("updates"), py::arg("mu"), py::arg("nu"), py::arg("dupdates"), py::arg("dmu_ext"), py::arg("dnu_ext"),
         py::arg("out"), py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("eps_root"), py::arg("count"),

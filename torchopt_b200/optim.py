@@ -208,7 +208,8 @@ def _fused_chain_step(step_op: AdamStep, params: list, grads: list, state: tuple
 class _FlatGroup:
     """The leaves of one (device, parameter dtype) group: where each lives in the flat moment buffers."""
 
-    __slots__ = ("index", "offsets", "numels", "shapes", "total", "device", "dtype", "state_dtype", "mu", "nu")
+    __slots__ = ("index", "offsets", "numels", "shapes", "total", "device", "dtype", "state_dtype", "mu", "nu",
+                 "cnt", "tables", "masks")
 
     def __init__(self, index: list, leaves: Sequence[torch.Tensor]) -> None:
         self.index = index
@@ -223,6 +224,8 @@ class _FlatGroup:
             total = (total + k + align - 1) // align * align
         self.total = total
         self.mu = self.nu = None
+        self.cnt = self.tables = None      # capturable: device step counts (int64 vector) + [c1, c2, o1, c2e] tables
+        self.masks = {}                    # capturable: device 0/1 vectors of the live-leaf patterns seen so far
 
 
 class FlatAdamState:
@@ -235,7 +238,15 @@ class FlatAdamState:
     4L and 3L, no per-leaf count tensors are built, and the outputs of a step come from one allocation.  Leaves that get
     no gradient in a step keep parameter, moments and count (the reference's skip semantics, adam_op.py:148-149)."""
 
-    def __init__(self, leaves: Sequence[torch.Tensor], moment_requires_grad: bool = False, *, _empty: bool = False):
+    def __init__(self, leaves: Sequence[torch.Tensor], moment_requires_grad: bool = False, *, _empty: bool = False,
+                 capturable: tuple | None = None):
+        """``capturable=(b1, b2, eps_root)``: the step counts live on the DEVICE and the bias corrections come from
+        host-computed device tables, so a differentiable step over this (persistent) state can be recorded in a CUDA
+        graph and every replay is one real step.  The state is then carried from step to step by VALUE: each step
+        reads the persistent moment buffers and writes its new moments back into them, so gradients flow through a
+        step (to parameters, gradients and the moments it read) but not from one step to the next -- the contract of
+        a one-step look-ahead (meta-gradient w.r.t. hyper-parameters of the current step, then ``stop_gradient``)."""
+        self.capturable = capturable
         self.num = len(leaves)
         self.signature = [(p.shape, p.dtype, p.device) for p in leaves]
         by_key: dict = {}
@@ -248,6 +259,14 @@ class FlatAdamState:
             for gr in self.groups:
                 gr.mu = torch.zeros(gr.total, dtype=gr.state_dtype, device=gr.device, requires_grad=moment_requires_grad)
                 gr.nu = torch.zeros(gr.total, dtype=gr.state_dtype, device=gr.device, requires_grad=moment_requires_grad)
+        if capturable is not None:
+            b1, b2, eps_root = capturable
+            for gr in self.groups:
+                if gr.device.type != "cuda":
+                    raise RuntimeError("Not implemented")     # no CPU path in this package
+                family = 1 if gr.state_dtype == torch.float64 else 0
+                gr.tables = [t.to(gr.device) for t in adam_op.bias_tables_ex(family, b1, b2, eps_root)]
+                gr.cnt = torch.zeros(len(gr.index), dtype=torch.int64, device=gr.device)
 
     def matches(self, leaves: Sequence[torch.Tensor]) -> bool:
         return len(leaves) == self.num and all(
@@ -257,6 +276,10 @@ class FlatAdamState:
     def step(self, hyper: tuple, params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor | None], *,
              inplace: bool = False, keep_grads: bool = False) -> list:
         """One whole optimizer step (recipe + Adam + scale + apply_updates); returns the new parameter list."""
+        if self.capturable is not None:
+            if inplace:
+                raise NotImplementedError("capturable=True with an in-place step: use Adam / FlatAdam(capturable=True)")
+            return self._step_capturable(hyper, params, grads)
         if not self.in_capture and capturing():
             # bias corrections are host scalars baked into the launch: same refusal as check_capturable
             raise RuntimeError(
@@ -283,6 +306,36 @@ class FlatAdamState:
         self.counts = after
         return new_p
 
+    def _step_capturable(self, hyper: tuple, params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor | None]) -> list:
+        b1, b2, eps, eps_root, step_size, wd_l2, wd_dec, maximize = hyper
+        new_p = list(params)
+        for gr in self.groups:
+            g_sel = [grads[i] for i in gr.index]
+            pattern = tuple(g is not None for g in g_sel)
+            if not any(pattern):
+                continue
+            if all(pattern):
+                gr.cnt.add_(1)                      # device-side increment, recorded with the graph
+            else:
+                mask = gr.masks.get(pattern)
+                if mask is None:                    # built from fills only, so that it can appear inside a capture too
+                    mask = torch.zeros(len(pattern), dtype=torch.int64, device=gr.device)
+                    for k, live in enumerate(pattern):
+                        if live:
+                            mask[k:k + 1].fill_(1)
+                    gr.masks[pattern] = mask
+                gr.cnt.add_(mask)
+            snap = gr.cnt.clone()                   # THIS step's counts: forward and backward read the same values
+            out, mu_new, nu_new = adam_op.flat_step(
+                [params[i] for i in gr.index], g_sel, gr.mu, gr.nu, gr.offsets, [0] * len(gr.index), b1, b2, eps,
+                eps_root, step_size, wd_l2, wd_dec, maximize, False, False, snap, gr.tables)
+            with torch.no_grad():                   # persistent state, carried by value (static addresses for replays)
+                gr.mu.copy_(mu_new)
+                gr.nu.copy_(nu_new)
+            for i, t in zip(gr.index, out):
+                new_p[i] = t
+        return new_p
+
     def to_leaf_state(self) -> ScaleByAdamState:
         """The reference layout: per-leaf ``mu`` / ``nu`` (views of the flat buffers, differentiable) and per-leaf
         0-dim int64 device ``count`` tensors tagged with their host value."""
@@ -293,6 +346,12 @@ class FlatAdamState:
                 mu[i] = gr.mu[off:off + k].view(shape)
                 nu[i] = gr.nu[off:off + k].view(shape)
                 devices[i] = gr.device
+        if self.capturable is not None:             # the counts ARE device memory: views of the count vectors
+            count = [None] * self.num
+            for gr in self.groups:
+                for k, i in enumerate(gr.index):
+                    count[i] = gr.cnt[k]
+            return ScaleByAdamState(mu=mu, nu=nu, count=count)
         return ScaleByAdamState(mu=mu, nu=nu, count=make_counts(list(self.counts), devices))
 
     @classmethod
@@ -359,8 +418,21 @@ class _AdamStateHolder:
     def load_state_dict(self, state: Any) -> None:
         self.state = state
 
+    _capturable: Any = None      # (b1, b2, eps_root) for MetaAdam / FuncAdam(capturable=True)
+
     def _flat_state(self, leaves: list, moment_requires_grad: bool) -> FlatAdamState:
         """The flat state for ``leaves``, converting from the reference layout if that is what is current."""
+        if self._capturable is not None:
+            # persistent by construction: the flat buffers ARE the state; what `state` shows are views of them
+            if self._flat is None:
+                if self._leaf is not None:
+                    raise NotImplementedError("capturable=True: load_state_dict is not supported (the state must keep "
+                                              "its device addresses)")
+                self._flat = FlatAdamState(leaves, moment_requires_grad, capturable=self._capturable)
+            elif not self._flat.matches(leaves):
+                raise ValueError("the parameters changed shape / dtype / device since the optimizer state was created")
+            self._leaf = None
+            return self._flat
         if self._leaf is not None and not (self._inplace_aliases and self._flat is not None):
             adam_state = next(st for st in self._leaf if isinstance(st, ScaleByAdamState))
             self._flat = FlatAdamState.from_leaf_state(leaves, adam_state)
@@ -445,11 +517,18 @@ class MetaAdam(_AdamStateHolder):
     # pylint: disable-next=too-many-arguments
     def __init__(self, module: nn.Module, lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 0.0, *, eps_root: float = 0.0,
-                 moment_requires_grad: bool = True, maximize: bool = False, use_accelerated_op: bool = True) -> None:
+                 moment_requires_grad: bool = True, maximize: bool = False, use_accelerated_op: bool = True,
+                 capturable: bool = False) -> None:
+        """``capturable=True``: a differentiable step over this optimizer's PERSISTENT state may be recorded in a CUDA graph
+        (device step counts + bias tables; see ``FlatAdamState``); the state is then carried between steps by value."""
         recipe = adamw if self.DECOUPLED else adam
         self.impl = recipe(lr, betas, eps, weight_decay, eps_root=eps_root, moment_requires_grad=moment_requires_grad,
                            maximize=maximize, use_accelerated_op=use_accelerated_op)
         self.fusable = not callable(lr)   # a schedule needs the chained scale_by_schedule, which is out of scope
+        if capturable:
+            if not self.fusable:
+                raise NotImplementedError("capturable=True needs a constant learning rate")
+            self._capturable = (betas[0], betas[1], eps_root)
         self.step_op = (AdamStep(betas[0], betas[1], eps, eps_root=eps_root, step_size=-lr, weight_decay=weight_decay,
                                  decoupled=self.DECOUPLED, maximize=maximize) if self.fusable else None)
         self.module = module
@@ -468,7 +547,7 @@ class MetaAdam(_AdamStateHolder):
         grads = torch.autograd.grad(loss, flat, create_graph=True, allow_unused=True)
         if PROFILE_HOST:
             h1 = time.perf_counter()
-        if self.fusable and FUSE_STEP and FLAT_STATE:
+        if self.fusable and ((FUSE_STEP and FLAT_STATE) or self._capturable is not None):
             new_params = self._flat_state(flat, self.moment_requires_grad).step(self.step_op.hyper, flat, grads)
         elif self.fusable and FUSE_STEP:
             new_params, self.state = _fused_chain_step(self.step_op, flat, list(grads), self._leaf_state(flat))
@@ -491,11 +570,16 @@ class FuncAdam(_AdamStateHolder):
     # pylint: disable-next=too-many-arguments
     def __init__(self, lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, *, eps_root: float = 0.0, moment_requires_grad: bool = False,
-                 maximize: bool = False, use_accelerated_op: bool = True) -> None:
+                 maximize: bool = False, use_accelerated_op: bool = True, capturable: bool = False) -> None:
+        """``capturable=True``: see ``MetaAdam``."""
         recipe = adamw if self.DECOUPLED else adam
         self.impl = recipe(lr, betas, eps, weight_decay, eps_root=eps_root, moment_requires_grad=moment_requires_grad,
                            maximize=maximize, use_accelerated_op=use_accelerated_op)
         self.fusable = not callable(lr)
+        if capturable:
+            if not self.fusable:
+                raise NotImplementedError("capturable=True needs a constant learning rate")
+            self._capturable = (betas[0], betas[1], eps_root)
         self.hyper = dict(b1=betas[0], b2=betas[1], eps=eps, eps_root=eps_root, step_size=-lr if self.fusable else 0.0,
                           weight_decay=weight_decay, decoupled=self.DECOUPLED, maximize=maximize)
         self.step_hyper = AdamStep(**self.hyper).hyper
@@ -503,7 +587,7 @@ class FuncAdam(_AdamStateHolder):
 
     def apply_gradients(self, grads: Sequence, params: Sequence, inplace: bool = False) -> list:
         params = list(params)
-        if self.fusable and FUSE_STEP and FLAT_STATE:
+        if self.fusable and ((FUSE_STEP and FLAT_STATE) or self._capturable is not None):
             flat = self._flat_state(params, self.moment_requires_grad)
             if inplace:   # the raw parameter values are updated; the reference writes through p.data (update.py:71-74)
                 with torch.no_grad():
