@@ -50,7 +50,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-total", type=int, default=N_TOTAL, help="elements of the whole flat state (default 2^30)")
-    ap.add_argument("--e2e-elems", type=int, default=1 << 27, help="elements per rank of the host-buffer e2e leg")
+    ap.add_argument("--e2e-elems", type=int, default=0,
+                    help="elements per rank of the host-buffer e2e leg (0 = the rank's whole shard if the host can pin it, "
+                         "else the largest power-of-two part of it that fits half of the available host memory)")
     ap.add_argument("--cpu-elems", type=int, default=1 << 26, help="elements of the bounded CPU-baseline sample")
     ap.add_argument("--e2e-slice", type=int, default=0, help="slice elements of the host pipeline (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -654,6 +656,43 @@ def public_api_flat(tb, abi, torch, n: int = 1 << 28, iters: int = 10) -> dict:
             "public_over_c_abi": ms_abi / ms_api, "gradients_bit_identical": same}
 
 
+def fp64_kernels(abi, torch, n: int = 1 << 26, iters: int = 20) -> dict:
+    """The fp64 instantiation of the fused kernels (the reference's CUDA tests are fp64-only): 48 / 72 algorithmic
+    bytes per element, timed like the headline kernels; ncu evidence that they are HBM-bound (FP64 pipe 13-22 % busy)
+    is in profiles/r02_fp64.md."""
+    dev = torch.device("cuda")
+    torch.manual_seed(5)
+    dt = torch.float64
+    t = {k: (torch.randn(n, device=dev) * sc).to(dt) for k, sc in (("g", 1e-2), ("mu", 1e-2), ("du", 1.0), ("dme", 1e-3),
+                                                                   ("dne", 1e-3))}
+    t["nu"] = (torch.rand(n, device=dev) * 1e-4).to(dt)
+    o = {k: torch.empty(n, device=dev, dtype=dt) for k in ("mu2", "nu2", "u", "dg", "dmu", "dnu")}
+    P = {k: v.data_ptr() for k, v in {**t, **o}.items()}
+    prep = abi.PreparedFused(abi.F64, [[P[k]] for k in ("g", "mu", "nu", "mu2", "nu2", "u")],
+                             [[P[k]] for k in ("du", "u", "mu2", "g", "dme", "dne", "dg", "dmu", "dnu")], [n], [COUNT], B1,
+                             B2, EPS, EPS_ROOT)
+    stream = torch.cuda.current_stream().cuda_stream
+    peak, _ = measured_peak()
+    res = {"workload": f"one flat leaf of {n} fp64 elements (arrays of {n * 8 >> 20} MiB)", "dtype": "f64"}
+    for name, fn, per_elem in (("forward", prep.forward, 48), ("backward", prep.backward, 72)):
+        for _ in range(3):
+            fn(stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn(stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        gbs = per_elem * n / (ms * 1e-3) / 1e9
+        res[name] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "avg_launch_ms": ms,
+                     "algorithmic_bytes_per_launch": per_elem * n}
+    total = res["forward"]["avg_launch_ms"] + res["backward"]["avg_launch_ms"]
+    res["gelem_per_s"] = n / (total * 1e-3) / 1e9
+    res["ncu"] = "profiles/r02_fp64.md: DRAM traffic 0.98x / 0.99x algorithmic, FP64 pipe 22 % / 13 % busy -> memory-bound"
+    return res
+
+
 def _load_example(name: str):
     import importlib.util
     spec = importlib.util.spec_from_file_location(f"b200_example_{name}", os.path.join(ROOT, "examples", f"{name}.py"))
@@ -726,6 +765,23 @@ def maml_task_parallel(tb, torch, dist, world: int, rank: int, local_rank: int, 
         runner.meta_grads_graphed(data, mine, T)     # records the task graphs (one instance per stream)
         graph = timed(runner.meta_grads_graphed, iters_graph)
         graph["instances"] = streams
+        # the dependency chain of ONE task (about 2 500 mostly tiny, dependent kernels) replayed alone on an otherwise idle
+        # GPU: the floor of a meta-iteration however many GPUs share the meta-batch
+        one = runner.task_graphs[0]
+        alone = float("inf")
+        for _ in range(5):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(one.stream):
+                a.record()
+                one.replay()
+                b.record()
+            torch.cuda.synchronize()
+            alone = min(alone, a.elapsed_time(b))
+        graph["single_task_replay_alone_ms"] = alone
+        graph["note"] = ("allreduce_us is bracketed by events around the one all_reduce and therefore includes waiting for "
+                         "the slowest rank; ms_per_meta_iter / tasks_per_rank vs single_task_replay_alone_ms shows how much "
+                         "the concurrently replayed task chains slow each other down")
         return {"workload": "MAML 5-way 5-shot, 32-task meta-batch, 5 inner MetaAdam steps, 75205-param CNN (14 leaves), "
                             "tasks split over ranks, one all-reduce of one flat fp32 bucket",
                 "n_gpus": world, "tasks_per_rank": len(mine), "bucket_bytes": int(sum(b.numel() * b.element_size()
@@ -734,6 +790,59 @@ def maml_task_parallel(tb, torch, dist, world: int, rank: int, local_rank: int, 
     finally:
         (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark,
          torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32) = flags
+
+
+def host_mem_available() -> int:
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 64 << 30
+
+
+def e2e_sample_elems(requested: int, shard: int, world: int) -> int:
+    """Elements per rank of the e2e leg: the whole shard when 12 pinned fp32 arrays of it fit half of the available host
+    memory (shared by the ranks of the box), else the largest power of two that does (at least 2^24)."""
+    if requested > 0:
+        return min(requested, shard)
+    budget = host_mem_available() // 2 // max(1, world) // 48     # 12 arrays x 4 bytes per element
+    if shard <= budget:
+        return shard
+    m = 1 << 24
+    while m * 2 <= budget and m * 2 <= shard:
+        m *= 2
+    return min(m, shard)
+
+
+def local_cpu_affinity(gpu_index: int):
+    """CPUs `nvidia-smi topo -m` lists as local to this GPU (its NUMA node), or None.  Pinned host memory is placed by
+    first touch: a rank that runs on its GPU's own NUMA node keeps its DMA traffic off the inter-socket link."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    import re
+    out = re.sub(r"\x1b\[[0-9;]*m", "", out)
+    header = None
+    for line in out.splitlines():
+        cells = [c.strip() for c in line.split("\t")]
+        if header is None and "CPU Affinity" in cells:
+            header = cells
+            continue
+        if header is not None and cells and cells[0] == f"GPU{gpu_index}":
+            # data rows have one more leading cell (the row label) than the header has before "CPU Affinity"
+            idx = header.index("CPU Affinity")
+            for cand in (cells[idx:idx + 2] if len(cells) > idx else []):
+                if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", cand or ""):
+                    cpus = set()
+                    for part in cand.split(","):
+                        lo, _, hi = part.partition("-")
+                        cpus.update(range(int(lo), int(hi or lo) + 1))
+                    return sorted(cpus)
+    return None
 
 
 def link_ceiling(torch, dev, mib: int = 512) -> dict:
@@ -857,11 +966,27 @@ def run_b200(args) -> None:
     # ---- e2e: public host-buffer API, pinned host arrays in and out, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        m = min(args.e2e_elems, n)
-        gen = torch.Generator().manual_seed(99 + rank)
-        hin = [torch.randn(m, generator=gen).mul_(s).pin_memory() for s in (1e-2, 1e-2, 1.0, 1.0, 1e-3, 1e-3)]
-        hin[2] = hin[2].abs_().mul_(1e-4)  # nu >= 0
-        hout = [torch.empty(m).pin_memory() for _ in range(6)]
+        # run on the CPUs local to this rank's GPU while the host arrays are allocated and touched (NUMA first touch)
+        affinity = local_cpu_affinity(local_rank)
+        old_affinity = os.sched_getaffinity(0)
+        if affinity and set(affinity) & old_affinity:
+            os.sched_setaffinity(0, set(affinity) & old_affinity)
+        m = e2e_sample_elems(args.e2e_elems, n, world)
+        hin = hout = None
+        while hin is None:
+            try:
+                gen = torch.Generator().manual_seed(99 + rank)
+                hin = []
+                for k, sc in enumerate((1e-2, 1e-2, 1e-4, 1.0, 1e-3, 1e-3)):
+                    a = torch.empty(m).pin_memory()
+                    torch.randn(m, generator=gen, out=a) if k != 2 else torch.rand(m, generator=gen, out=a)  # nu >= 0
+                    hin.append(a.mul_(sc))
+                hout = [torch.empty(m).pin_memory() for _ in range(6)]
+            except RuntimeError:      # the host refused to page-lock that much: halve the sample
+                hin = hout = None
+                if m <= (1 << 24):
+                    raise
+                m //= 2
 
         def host_step():
             tb.adam_op.host_step(hin[0], hin[1], hin[2], hin[3], hin[4], hin[5], hout, B1, B2, EPS, EPS_ROOT, COUNT,
@@ -869,7 +994,7 @@ def run_b200(args) -> None:
 
         for _ in range(2):
             host_step()
-        e2e_steps = max(3, min(K, 10))
+        e2e_steps = max(3, min(K, 10)) if m <= (1 << 28) else 4
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -880,10 +1005,16 @@ def run_b200(args) -> None:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": m * world * e2e_steps / float(dt.item()) / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": 6 * 4 * m, "d2h_bytes_per_step": 6 * 4 * m, "steps": e2e_steps,
-               "sample": f"{m} elements per rank per step (sub-range of the rank's shard; the path is PCIe-bound and "
-                         f"size-independent), API torchopt_b200.adam_op.host_step -> b200_adam_host_step_f32"}
+               "frac_of_shard": m / n,
+               "sample": (f"{m} of the rank's {n} elements per step" + (" (the whole shard)" if m == n else
+                          " (what half of the available host memory lets the ranks page-lock; the path is "
+                          "PCIe-bound and size-independent)") +
+                          ", API torchopt_b200.adam_op.host_step -> b200_adam_host_step_f32"),
+               "cpu_affinity": (f"{len(set(affinity) & old_affinity)} CPUs local to GPU {local_rank} "
+                                f"(nvidia-smi topo -m)" if affinity and set(affinity) & old_affinity else "unchanged")}
         tb._C.host_release()
         del hin, hout
+        os.sched_setaffinity(0, old_affinity)
         if rank == 0 and world == 1:
             e2e["link"] = link_ceiling(torch, dev)
             e2e["link"]["frac"] = e2e["value"] / e2e["link"]["ceiling_gelem_per_s"]
@@ -897,6 +1028,7 @@ def run_b200(args) -> None:
         side = [("maml_task_parallel", lambda: maml_task_parallel(tb, torch, dist, world, rank, local_rank))]  # every N
         if world == 1:
             side += [("public_api_flat", lambda: public_api_flat(tb, abi, torch)),
+                     ("roofline_f64", lambda: fp64_kernels(abi, torch)),
                      ("resnet18_unroll5", lambda: resnet18_unroll(tb, torch)),
                      ("whole_step_kernels", lambda: whole_step_kernels(abi, torch)),
                      ("config0_mlp1m", lambda: config0_mlp1m(tb, torch))]

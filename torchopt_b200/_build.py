@@ -95,6 +95,8 @@ def build_tools(force: bool = False, verbose: bool = True) -> list[str]:
             # linked against the product library (some tools time their variant against the product kernel)
             cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
                    "--fmad=false", f"-I{INCLUDE}", f"-I{CSRC}", src, f"-L{PKG}", "-lb200adam",
+                   # driver API (tools/guard_pages.cu: virtual memory management); the stub only satisfies the linker
+                   f"-L{os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'lib64', 'stubs')}", "-lcuda",
                    "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../torchopt_b200", "-o", exe]
             if verbose:
                 print("[torchopt_b200] " + " ".join(cmd), flush=True)
