@@ -13,6 +13,11 @@ backward launch (du, u, mu', g, dmu_ext, dnu_ext -> dg, dmu, dnu; 36 B/elem) ove
 bytes per element.  Inputs are synthetic, resident in HBM before the timed region; every array is
 >> L2 (126 MB), so no L2 flush is needed between iterations.
 
+Round 2: the timed region holds nothing but the 2K launches (every launch carries the programmatic-dependent-launch
+attribute; an event between the two kernels of a step would break their overlap) -- the per-kernel durations behind
+`roofline` come from a second pass over the same K steps with an event after every launch.  `e2e` runs over the rank's whole
+shard when the host can page-lock it.  `extra` (N = 1; `maml_task_parallel` at every N) holds the secondary BASELINE configs.
+
 Prints ONE JSON line (rank 0).  `value` = elements of the whole job processed per second by fwd+bwd, timed on the
 device with CUDA events on the launching stream, max over ranks.  `roofline` is for the dominant kernel (backward).
 `e2e` is the same metric through the public host-buffer API (pinned host arrays in, host arrays out; pipelined

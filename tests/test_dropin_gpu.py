@@ -1,7 +1,8 @@
 """Drop-in acceptance: the reference's OWN Python package and its OWN tests on top of this repo's native module.
 
-``oracle/_ref/dropin/`` (staged by tests/dropin/stage.py from /root/reference; git-ignored, travels to the GPU box)
-holds an unmodified copy of ``torchopt/`` and of the reference test files that touch the Adam path.  Here the
+``oracle/_ref/dropin.tar.gz`` (packed by tests/dropin/stage.py from /root/reference; git-ignored, travels to the GPU box)
+holds an unmodified copy of ``torchopt/`` and of the reference test files that touch the Adam path.  Here it is unpacked
+into a scratch directory, the
 freshly built ``torchopt_b200/_C.so`` + ``libb200adam.so`` are placed inside that package as ``torchopt/_C.so`` -- the
 exact swap INTEGRATION.md describes -- and the reference's tests run in a subprocess:
 
@@ -30,8 +31,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-STAGE = os.path.join(ROOT, "oracle", "_ref", "dropin")
+ARCHIVE = os.path.join(ROOT, "oracle", "_ref", "dropin.tar.gz")
 SHIMS = os.path.join(ROOT, "tests", "dropin", "shims")
+STAGE = ""     # scratch directory the archive is unpacked into (once per session, see _need_stage)
 PKG = os.path.join(ROOT, "torchopt_b200")
 
 pytestmark = pytest.mark.gpu
@@ -46,8 +48,18 @@ NOT_ACCELERATED = "use_accelerated_op(False)"
 
 
 def _need_stage() -> None:
-    if not os.path.isdir(os.path.join(STAGE, "reftests")):
-        pytest.skip("drop-in stage missing: run __graft_entry__.build() where /root/reference is mounted")
+    global STAGE
+    if STAGE:
+        return
+    if not os.path.isfile(ARCHIVE):
+        pytest.skip("drop-in archive missing: run __graft_entry__.build() where /root/reference is mounted")
+    import atexit
+    import tarfile
+    import tempfile
+    STAGE = tempfile.mkdtemp(prefix="b200_dropin_")
+    atexit.register(shutil.rmtree, STAGE, ignore_errors=True)
+    with tarfile.open(ARCHIVE) as tar:
+        tar.extractall(STAGE)
 
 
 def _install_native(variant: str) -> str:
