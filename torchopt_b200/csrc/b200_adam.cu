@@ -94,18 +94,6 @@ struct HostLeaf {
   typename Op::CT ls[Op::NLS > 0 ? Op::NLS : 1];
 };
 
-template <class Op, int P, int U, int BLOCK, int MAXL>
-static int occupancy_ctas_per_sm() {
-  static std::atomic<int> cached{0};
-  int v = cached.load(std::memory_order_relaxed);
-  if (v > 0) return v;
-  int nb = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, stream_kernel<Op, P, U, BLOCK, MAXL>, BLOCK, 0);
-  if (e != cudaSuccess || nb <= 0) nb = 1;
-  cached.store(nb, std::memory_order_relaxed);
-  return nb;
-}
-
 template <class Op, int P, int U, int BLOCK>
 static int pick_chunk_elems(long long total_elems, int sms) {
   constexpr int TILE = BLOCK * P * U;
