@@ -22,10 +22,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT_DIR = os.path.join(ROOT, "build", "tune")
 L2_POLICIES = {"none": ("", ""), "ldEF": (".L2::evict_first", ""), "stEF": ("", ".L2::evict_first"),
-               "ldstEF": (".L2::evict_first", ".L2::evict_first")}
+               "ldstEF": (".L2::evict_first", ".L2::evict_first"),
+               # round 4: L2 prefetch-size hints on the loads (the sector group the L2 fetches from DRAM per miss)
+               "ld256B": (".L2::256B", ""), "ld128B": (".L2::128B", ""), "ld64B": (".L2::64B", "")}
 if os.environ.get("TUNE_ROUND", "2") == "1":   # round-1 sweep: vector width / unroll / CTA size
     VARIANTS = [(p, u, b, "none") for p, u in ((4, 1), (4, 2), (4, 4), (8, 1), (8, 2), (8, 4)) for b in (128, 256, 512)]
     RUNTIME = [(c, t) for c in (0, 1, 2, 4, 8, 16) for t in (1, 2, 4, 8)]
+elif os.environ.get("TUNE_ROUND", "2") == "4":  # L2 prefetch-size hints on the shipped large-launch shapes
+    VARIANTS = [(8, u, 512, pol) for u in (1, 2) for pol in ("none", "ld256B", "ld128B", "ld64B")]
+    RUNTIME = [(0, 1)]
 elif os.environ.get("TUNE_ROUND", "2") == "3":  # mid-size leaves (2^20..2^26): CTA size / unroll vs the last-wave tail
     VARIANTS = [(8, u, b, "none") for u in (1, 2) for b in (128, 256, 512)]
     RUNTIME = [(0, 1), (4, 1), (8, 1), (16, 1)]
