@@ -661,25 +661,29 @@ def public_api_flat(tb, abi, torch, n: int = 1 << 28, iters: int = 10) -> dict:
             "public_over_c_abi": ms_abi / ms_api, "gradients_bit_identical": same}
 
 
-def fp64_kernels(abi, torch, n: int = 1 << 26, iters: int = 20) -> dict:
-    """The fp64 instantiation of the fused kernels (the reference's CUDA tests are fp64-only): 48 / 72 algorithmic
-    bytes per element, timed like the headline kernels; ncu evidence that they are HBM-bound (FP64 pipe 13-22 % busy)
-    is in profiles/r02_fp64.md."""
+def variant_kernels(abi, torch, variant: str, n: int, iters: int = 20) -> dict:
+    """The other two dtype families of the fused kernels, timed like the headline kernels:
+    "f64"  -- the reference's CUDA tests are fp64-only; 48 / 72 algorithmic bytes per element; ncu evidence that the
+              kernels are HBM-bound (FP64 pipe 13-22 % busy) is in profiles/r02_fp64.md;
+    "bf16" -- bf16 gradient-side arrays (g, u, du, dg) + fp32 moments, the mixed-precision variant north_star names:
+              20 / 30 algorithmic bytes per element."""
     dev = torch.device("cuda")
     torch.manual_seed(5)
-    dt = torch.float64
-    t = {k: (torch.randn(n, device=dev) * sc).to(dt) for k, sc in (("g", 1e-2), ("mu", 1e-2), ("du", 1.0), ("dme", 1e-3),
-                                                                   ("dne", 1e-3))}
-    t["nu"] = (torch.rand(n, device=dev) * 1e-4).to(dt)
-    o = {k: torch.empty(n, device=dev, dtype=dt) for k in ("mu2", "nu2", "u", "dg", "dmu", "dnu")}
+    gd, sd, dtype_id, b_fwd, b_bwd = ((torch.float64, torch.float64, abi.F64, 48, 72) if variant == "f64" else
+                                      (torch.bfloat16, torch.float32, abi.BF16_F32, 20, 30))
+    t = {"g": (torch.randn(n, device=dev) * 1e-2).to(gd), "mu": (torch.randn(n, device=dev) * 1e-2).to(sd),
+         "nu": (torch.rand(n, device=dev) * 1e-4).to(sd), "du": torch.randn(n, device=dev).to(gd),
+         "dme": (torch.randn(n, device=dev) * 1e-3).to(sd), "dne": (torch.randn(n, device=dev) * 1e-3).to(sd)}
+    o = {k: torch.empty(n, device=dev, dtype=gd if k in ("u", "dg") else sd) for k in ("mu2", "nu2", "u", "dg", "dmu", "dnu")}
     P = {k: v.data_ptr() for k, v in {**t, **o}.items()}
-    prep = abi.PreparedFused(abi.F64, [[P[k]] for k in ("g", "mu", "nu", "mu2", "nu2", "u")],
+    prep = abi.PreparedFused(dtype_id, [[P[k]] for k in ("g", "mu", "nu", "mu2", "nu2", "u")],
                              [[P[k]] for k in ("du", "u", "mu2", "g", "dme", "dne", "dg", "dmu", "dnu")], [n], [COUNT], B1,
                              B2, EPS, EPS_ROOT)
     stream = torch.cuda.current_stream().cuda_stream
     peak, _ = measured_peak()
-    res = {"workload": f"one flat leaf of {n} fp64 elements (arrays of {n * 8 >> 20} MiB)", "dtype": "f64"}
-    for name, fn, per_elem in (("forward", prep.forward, 48), ("backward", prep.backward, 72)):
+    res = {"workload": f"one flat leaf of {n} elements, {'fp64' if variant == 'f64' else 'bf16 gradients + fp32 moments'}",
+           "dtype": variant}
+    for name, fn, per_elem in (("forward", prep.forward, b_fwd), ("backward", prep.backward, b_bwd)):
         for _ in range(3):
             fn(stream)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -694,7 +698,8 @@ def fp64_kernels(abi, torch, n: int = 1 << 26, iters: int = 20) -> dict:
                      "algorithmic_bytes_per_launch": per_elem * n}
     total = res["forward"]["avg_launch_ms"] + res["backward"]["avg_launch_ms"]
     res["gelem_per_s"] = n / (total * 1e-3) / 1e9
-    res["ncu"] = "profiles/r02_fp64.md: DRAM traffic 0.98x / 0.99x algorithmic, FP64 pipe 22 % / 13 % busy -> memory-bound"
+    if variant == "f64":
+        res["ncu"] = "profiles/r02_fp64.md: DRAM traffic 0.98x / 0.99x algorithmic, FP64 pipe 22 % / 13 % busy -> memory-bound"
     return res
 
 
@@ -1033,7 +1038,8 @@ def run_b200(args) -> None:
         side = [("maml_task_parallel", lambda: maml_task_parallel(tb, torch, dist, world, rank, local_rank))]  # every N
         if world == 1:
             side += [("public_api_flat", lambda: public_api_flat(tb, abi, torch)),
-                     ("roofline_f64", lambda: fp64_kernels(abi, torch)),
+                     ("roofline_f64", lambda: variant_kernels(abi, torch, "f64", 1 << 26)),
+                     ("roofline_bf16", lambda: variant_kernels(abi, torch, "bf16", 1 << 28)),
                      ("resnet18_unroll5", lambda: resnet18_unroll(tb, torch)),
                      ("whole_step_kernels", lambda: whole_step_kernels(abi, torch)),
                      ("config0_mlp1m", lambda: config0_mlp1m(tb, torch))]
