@@ -275,3 +275,75 @@ def test_differentiable_step_with_persistent_state_recorded_in_a_cuda_graph():
             assert torch.equal(x, y), f"replay {k} differs from eager step {WARM + k + 1}"
     st = next(s for s in opt_c.state if isinstance(s, tb.ScaleByAdamState))
     assert [int(c) for c in st.count] == [WARM + K] * len(SIZES)
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_capturable_differentiable_abi_vs_oracle_at_any_count(c_oracle, tag):
+    """Raw C ABI of the capturable DIFFERENTIABLE step (b200_adam_step_forward_capturable / _backward_capturable): device
+    count + four tables vs the oracle's whole-step forward and backward, for counts inside the tables, at their end and
+    far beyond; full and partial presence of the incoming gradients; two leaves with different counts in one launch."""
+    from oracle import adam_oracle as ao
+    from torchopt_b200 import abi
+    import torchopt_b200 as tb
+    dt, npdt = (abi.F32, np.float32) if tag == "f32" else (abi.F64, np.float64)
+    b1, b2, eps, er, lr = 0.9, 0.999, 1e-8, 1e-8, 3e-3
+    tabs = [t.cuda() for t in tb.adam_op.bias_tables_ex(1 if tag == "f64" else 0, b1, b2, er)]
+    T = tabs[0].numel()
+    rng = np.random.default_rng(9)
+    s = torch.cuda.current_stream().cuda_stream
+    lib = abi.load()
+    ptrs, arr = abi._ptrs, abi._arr
+    sizes = (1023, 70_001)
+    for counts in ((1, 7), (T - 1, T), (T + 1, 10**6), (2**40, 3)):
+        leaves = []
+        for n, count in zip(sizes, counts):
+            a = dict(p=(rng.standard_normal(n) * 0.3).astype(npdt), g=(rng.standard_normal(n) * 1e-2).astype(npdt),
+                     mu=(rng.standard_normal(n) * 1e-2).astype(npdt), nu=(rng.random(n) * 1e-4).astype(npdt),
+                     dp=rng.standard_normal(n).astype(npdt), dme=(rng.standard_normal(n) * 1e-3).astype(npdt),
+                     dne=(rng.standard_normal(n) * 1e-3).astype(npdt))
+            a["g"][::11] = 0
+            a["mu"][::11] = 0
+            leaves.append((n, count, a, {k: torch.from_numpy(v).cuda() for k, v in a.items()}))
+        cnt = torch.tensor(list(counts), dtype=torch.int64, device="cuda")
+        cptr = [cnt.data_ptr(), cnt.data_ptr() + 8]
+        outs = [{k: torch.full((n,), 7.0, device="cuda", dtype=torch.float64 if tag == "f64" else torch.float32)
+                 for k in ("p2", "mu2", "nu2", "dg", "dmu", "dnu")} for n, _, _, _ in leaves]
+        col = lambda k: ptrs([d[k].data_ptr() for _, _, _, d in leaves])        # noqa: E731
+        ocol = lambda k: ptrs([o[k].data_ptr() for o in outs])                   # noqa: E731
+        ns = arr(abi.c_int64, list(sizes))
+        rc = lib.b200_adam_step_forward_capturable(dt, 2, col("p"), col("g"), col("mu"), col("nu"), ocol("p2"), ocol("mu2"),
+                                                   ocol("nu2"), None, ns, ptrs(cptr), tabs[0].data_ptr(), tabs[1].data_ptr(),
+                                                   T, b1, b2, eps, er, -lr, 0.0, 0.0, 0, s)
+        assert rc == 0
+        torch.cuda.synchronize()
+        want_fwd = []
+        for (n, count, a, _), o in zip(leaves, outs):
+            w_p, w_mu, w_nu, _ = ao.fused_step_forward(c_oracle, a["p"], a["g"], a["mu"], a["nu"], b1, b2, eps, er, count, -lr)
+            want_fwd.append((w_mu, w_nu))
+            what = f"capturable step forward n={n} count={count}"
+            assert_bits_equal(o["p2"].cpu().numpy(), w_p, what + " p'")
+            assert_bits_equal(o["mu2"].cpu().numpy(), w_mu, what + " mu'")
+            assert_bits_equal(o["nu2"].cpu().numpy(), w_nu, what + " nu'")
+        for hme, hne in ((1, 1), (0, 0), (1, 0)):
+            dme = ptrs([d["dme"].data_ptr() if hme else None for _, _, _, d in leaves])
+            dne = ptrs([d["dne"].data_ptr() if hne else None for _, _, _, d in leaves])
+            rc = lib.b200_adam_step_backward_capturable(
+                dt, 2, col("dp"), None, ocol("mu2"), ocol("nu2"), col("g"), dme, dne, ocol("dg"), ocol("dmu"), ocol("dnu"),
+                None, None, ns, ptrs(cptr), tabs[0].data_ptr(), tabs[1].data_ptr(), tabs[2].data_ptr(), tabs[3].data_ptr(), T,
+                b1, b2, eps, er, -lr, 0.0, 0.0, 0, s)
+            assert rc == 0
+            torch.cuda.synchronize()
+            for (n, count, a, _), o, (w_mu, w_nu) in zip(leaves, outs, want_fwd):
+                want = ao.fused_step_backward(c_oracle, a["dp"], w_mu, w_nu, a["g"], a["dme"] if hme else None,
+                                              a["dne"] if hne else None, b1, b2, eps, er, count, -lr)
+                for k, name in enumerate(("dg", "dmu", "dnu")):
+                    assert_bits_equal(o[name].cpu().numpy(), want[k],
+                                      f"capturable step backward {name} n={n} count={count} pattern={(hme, hne)}")
+    # argument errors: a missing table / count pointer is refused, not dereferenced
+    assert lib.b200_adam_step_forward_capturable(dt, 2, col("p"), col("g"), col("mu"), col("nu"), ocol("p2"), ocol("mu2"),
+                                                 ocol("nu2"), None, ns, ptrs([cptr[0], None]), tabs[0].data_ptr(),
+                                                 tabs[1].data_ptr(), T, b1, b2, eps, er, -lr, 0.0, 0.0, 0, s) == -2
+    assert lib.b200_adam_step_backward_capturable(dt, 2, col("dp"), None, ocol("mu2"), ocol("nu2"), col("g"), dme, dne,
+                                                  ocol("dg"), ocol("dmu"), ocol("dnu"), None, None, ns, ptrs(cptr),
+                                                  tabs[0].data_ptr(), tabs[1].data_ptr(), None, tabs[3].data_ptr(), T, b1, b2,
+                                                  eps, er, -lr, 0.0, 0.0, 0, s) == -2
