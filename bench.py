@@ -58,7 +58,9 @@ def parse_args():
     ap.add_argument("--e2e-elems", type=int, default=0,
                     help="elements per rank of the host-buffer e2e leg (0 = the rank's whole shard if the host can pin it, "
                          "else the largest power-of-two part of it that fits half of the available host memory)")
-    ap.add_argument("--cpu-elems", type=int, default=1 << 26, help="elements of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-elems", type=int, default=0,
+                    help="elements of the bounded CPU sample (0 = as much of the 2^30 workload as fits the time budget of "
+                         "the leg and a third of the host's free memory; a power of two, at least 2^24)")
     ap.add_argument("--e2e-slice", type=int, default=0, help="slice elements of the host pipeline (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -218,12 +220,30 @@ def time_cpu(step, t, reps: int, warmup: int) -> float:
     return best
 
 
+def cpu_sample_elems(requested: int, n_total: int, step, steps_to_run: int, budget_s: float) -> int:
+    """How much of the workload one CPU step covers: the whole n_total when `steps_to_run` such steps fit `budget_s`
+    seconds (rate calibrated on a 2^24-element step) and a third of the free host memory (15 fp32 arrays live at once),
+    else the largest power of two that does."""
+    if requested > 0:
+        return min(requested, n_total)
+    probe = min(1 << 24, n_total)
+    t = cpu_inputs(probe)
+    rate = probe / time_cpu(step, t, reps=2, warmup=1)           # elements per second
+    by_time = rate * budget_s / max(1, steps_to_run)
+    by_mem = host_mem_available() / 3 / (15 * 4)
+    cap = min(n_total, by_time, by_mem)
+    n = probe
+    while n * 2 <= cap:
+        n *= 2
+    return n_total if n_total <= cap else n
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = min(args.cpu_elems, args.n_total)
     step, kind, cores = load_cpu_impl()
+    n = cpu_sample_elems(args.cpu_elems, args.n_total, step, max(1, args.steps) + max(1, min(args.warmup, 3)), 120.0)
     t = cpu_inputs(n)
     for _ in range(max(1, min(args.warmup, 3))):
         step(t)
@@ -233,7 +253,9 @@ def run_reference(args) -> None:
         step(t)
     dt = time.perf_counter() - t0
     value = n * steps / dt / 1e9
-    sample = f"{n} of {args.n_total} elements per step (bounded sample), un-fused 6 ops + 3 adds as autograd runs them"
+    sample = (f"{n} of {args.n_total} elements per step" + (" (the whole workload)" if n == args.n_total else
+              " (the largest power of two that keeps the run within ~2 minutes and a third of the host's free memory)") +
+              ", un-fused 6 ops + 3 adds as autograd runs them")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -1055,7 +1077,7 @@ def run_b200(args) -> None:
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         step_cpu, kind, cores = load_cpu_impl()
-        m = min(args.cpu_elems, args.n_total)
+        m = cpu_sample_elems(args.cpu_elems, args.n_total, step_cpu, 7 + 7, 25.0)   # 2+5 runs of the step, 2+5 of forward_
         cpu_t = cpu_inputs(m)
         best = time_cpu(step_cpu, cpu_t, reps=5, warmup=2)
         cpu_baseline = {"value": m / best / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
