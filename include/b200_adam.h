@@ -43,7 +43,9 @@
 extern "C" {
 #endif
 
-#define B200_ADAM_ABI_VERSION 1
+/* 1: round 1.  2: additive -- b200_adam_set_pdl, b200_adam_step_forward_capturable / _backward_capturable,
+ * b200_adam_bias_table_len_ex / _ex (nothing of version 1 changed its signature or meaning). */
+#define B200_ADAM_ABI_VERSION 2
 
 enum b200_adam_dtype { B200_ADAM_F32 = 0, B200_ADAM_F64 = 1, B200_ADAM_BF16_F32 = 2 };
 

@@ -36,7 +36,7 @@ def test_header_symbols_all_exported_and_typed():
 def test_abi_version_and_error_strings_without_gpu():
     from torchopt_b200 import abi
     lib = abi.load()
-    assert lib.b200_adam_abi_version() == 1
+    assert lib.b200_adam_abi_version() == 2
     assert lib.b200_adam_error_string(0) == b"ok"
     assert b"dtype" in lib.b200_adam_error_string(-1)
     assert b"argument" in lib.b200_adam_error_string(-2)
