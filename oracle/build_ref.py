@@ -116,8 +116,57 @@ def build_cuda(force: bool = False, verbose: bool = True) -> str | None:
     return CUDA_OUT
 
 
+HYBRID_OUT_DIR = os.path.join(OUT_DIR, "hybrid")
+HYBRID_OUT = os.path.join(HYBRID_OUT_DIR, "_C.so")
+HYBRID_DISPATCHER = os.path.join(os.path.dirname(HERE), "tests", "dropin", "maintainer_adam_op.cpp")
+HYBRID_REF_SOURCES = ["src/extension.cpp", "src/adam_op/adam_op_impl_cpu.cpp"]
+
+
+def build_hybrid(force: bool = False, verbose: bool = True) -> str | None:
+    """INTEGRATION.md section 2, compiled: the reference's UNMODIFIED module entry (src/extension.cpp) and CPU kernels
+    (src/adam_op/adam_op_impl_cpu.cpp) + tests/dropin/maintainer_adam_op.cpp (our re-pointed dispatcher, standing in for the
+    reference's src/adam_op/adam_op.cpp) linked against torchopt_b200/libb200adam.so -> oracle/_ref/hybrid/_C.so.
+    This is the module a TorchOpt maintainer ships after the integration: TorchOpt's own kernels for CPU tensors, this repo's
+    for CUDA tensors.  Test infrastructure (tests/test_dropin_gpu.py); the product never loads it."""
+    pkg = os.path.join(os.path.dirname(HERE), "torchopt_b200")
+    lib = os.path.join(pkg, "libb200adam.so")
+    if not all(os.path.isfile(os.path.join(REF, s)) for s in HYBRID_REF_SOURCES) or not os.path.isfile(lib):
+        return HYBRID_OUT if os.path.isfile(HYBRID_OUT) else None
+    deps = [os.path.join(REF, s) for s in HYBRID_REF_SOURCES] + [HYBRID_DISPATCHER, lib,
+                                                                os.path.join(os.path.dirname(HERE), "include", "b200_adam.h")]
+    if not force and os.path.isfile(HYBRID_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(HYBRID_OUT) for d in deps):
+        return HYBRID_OUT
+    import pybind11
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    os.makedirs(HYBRID_OUT_DIR, exist_ok=True)
+    torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    inc = [REF, os.path.join(os.path.dirname(HERE), "include"), pybind11.get_include(), sysconfig.get_paths()["include"],
+           *ce.include_paths(), "/usr/local/cuda/include"]
+    defs = [f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", "-DTORCH_API_INCLUDE_EXTENSION_H",
+            "-DTORCH_EXTENSION_NAME=_C"]
+    objs = []
+    for src in [os.path.join(REF, s) for s in HYBRID_REF_SOURCES] + [HYBRID_DISPATCHER]:
+        obj = os.path.join(HYBRID_OUT_DIR, os.path.basename(src) + ".o")
+        cmd = ["g++", "-std=c++17", "-O3", "-fopenmp", "-fPIC", "-w", *defs, *[f"-I{p}" for p in inc], "-c", src, "-o", obj]
+        if verbose:
+            print("[oracle/_ref/hybrid] g++ ...", src, flush=True)
+        subprocess.check_call(cmd)
+        objs.append(obj)
+    link = ["g++", "-shared", *objs, "-o", HYBRID_OUT, f"-L{pkg}", "-lb200adam", "-Wl,-rpath,$ORIGIN:$ORIGIN/../../../torchopt_b200",
+            f"-L{torch_lib}", f"-Wl,-rpath,{torch_lib}", "-ltorch_python", "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10",
+            "-lc10_cuda", "-L/usr/lib/gcc/x86_64-linux-gnu/13", "-lgomp"]
+    subprocess.check_call(link)
+    for o in objs:
+        os.remove(o)
+    return HYBRID_OUT
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv)
     print(path if path else "reference sources not present and no prebuilt oracle/_ref/_C.so")
     if "--cuda" in sys.argv:
         print(build_cuda(force="--force" in sys.argv))
+    if "--hybrid" in sys.argv:
+        print(build_hybrid(force="--force" in sys.argv))
