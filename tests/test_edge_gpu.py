@@ -133,3 +133,38 @@ def test_cuda_graph_capture_and_side_stream():
     for a, b, c in zip(eager, on_side, captured):
         for x, y, z in zip(a, b, c):
             assert torch.equal(x, y) and torch.equal(x, z)
+
+
+@pytest.mark.gpu
+def test_prepared_launch_handle_equals_per_call_arguments():
+    """b200_adam_prepare_fused / _launch_prepared / _release_prepared: the argument block kept on the library side gives
+    the same launches as passing every argument per call (two leaves, ragged sizes); invalid arguments give NULL / E_ARG."""
+    import torch
+    from torchopt_b200 import abi
+    lib = abi.load()
+    sizes = [1000, 70_001]
+    gen = torch.Generator("cuda").manual_seed(4)
+    t = {k: [torch.randn(n, device="cuda", generator=gen) * sc for n in sizes]
+         for k, sc in (("g", 1e-2), ("mu", 1e-2), ("du", 1.0), ("dme", 1e-3), ("dne", 1e-3))}
+    t["nu"] = [torch.rand(n, device="cuda", generator=gen) * 1e-4 for n in sizes]
+    outs = [{k: [torch.full((n,), 7.0, device="cuda") for n in sizes] for k in ("mu2", "nu2", "u", "dg", "dmu", "dnu")}
+            for _ in range(2)]
+    P = lambda d, k: [x.data_ptr() for x in d[k]]   # noqa: E731
+    s = torch.cuda.current_stream().cuda_stream
+    preps = []
+    for o in outs:
+        preps.append(abi.PreparedFused(
+            abi.F32, [P(t, "g"), P(t, "mu"), P(t, "nu"), P(o, "mu2"), P(o, "nu2"), P(o, "u")],
+            [P(t, "du"), P(o, "u"), P(o, "mu2"), P(t, "g"), P(t, "dme"), P(t, "dne"), P(o, "dg"), P(o, "dmu"), P(o, "dnu")],
+            sizes, [3, 9], 0.9, 0.999, 1e-8, 1e-8))
+    assert preps[0].handle and preps[1].handle
+    preps[1].lib.b200_adam_release_prepared(preps[1].handle)
+    preps[1].handle = None                          # second instance: the per-call path
+    for p in preps:
+        assert p.forward(s) == 0 and p.backward(s) == 0
+    torch.cuda.synchronize()
+    for k in outs[0]:
+        for a, b in zip(outs[0][k], outs[1][k]):
+            assert torch.equal(a, b) and not (a == 7.0).all(), k
+    assert lib.b200_adam_launch_prepared(None, 0, s) == -2
+    assert not lib.b200_adam_prepare_fused(abi.F32, 0, *([None] * 12), None, None, 0.9, 0.999, 1e-8, 0.0)

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cmath>
 #include <type_traits>
+#include <vector>
 
 #include "adam_kernels.cuh"
 
@@ -921,6 +922,54 @@ int b200_adam_step_backward(int dtype, int64_t num_leaves, const void *const *dp
   if (dtype == B200_ADAM_F32) B200_STEP_BWD_DT(float, float, float);
 #undef B200_STEP_BWD_DT
   return B200_ADAM_E_DTYPE;
+}
+
+// ---- prepared launches: the argument block of a fused forward + backward pair kept on the library side ------------
+struct PreparedPair {
+  int dtype;
+  int64_t L;
+  std::vector<const void *> g, mu, nu, du, u, new_mu, dmu_ext, dnu_ext;
+  std::vector<void *> mu_out, nu_out, u_out, dg, dmu, dnu;
+  std::vector<int64_t> n;
+  std::vector<uint64_t> count;
+  double b1, b2, eps, eps_root;
+};
+
+void *b200_adam_prepare_fused(int dtype, int64_t num_leaves, const void *const *g, const void *const *mu,
+                              const void *const *nu, void *const *mu_out, void *const *nu_out, void *const *u_out,
+                              const void *const *du, const void *const *dmu_ext, const void *const *dnu_ext, void *const *dg,
+                              void *const *dmu, void *const *dnu, const int64_t *n, const uint64_t *count, double b1,
+                              double b2, double eps, double eps_root) {
+  if (num_leaves <= 0 || !g || !mu || !nu || !mu_out || !nu_out || !u_out || !du || !dmu_ext || !dnu_ext || !dg || !dmu ||
+      !dnu || !n || !count)
+    return nullptr;
+  auto *p = new PreparedPair();
+  p->dtype = dtype, p->L = num_leaves, p->b1 = b1, p->b2 = b2, p->eps = eps, p->eps_root = eps_root;
+  const size_t L = (size_t)num_leaves;
+  p->g.assign(g, g + L), p->mu.assign(mu, mu + L), p->nu.assign(nu, nu + L);
+  p->mu_out.assign(mu_out, mu_out + L), p->nu_out.assign(nu_out, nu_out + L), p->u_out.assign(u_out, u_out + L);
+  p->du.assign(du, du + L), p->dmu_ext.assign(dmu_ext, dmu_ext + L), p->dnu_ext.assign(dnu_ext, dnu_ext + L);
+  p->dg.assign(dg, dg + L), p->dmu.assign(dmu, dmu + L), p->dnu.assign(dnu, dnu + L);
+  p->n.assign(n, n + L), p->count.assign(count, count + L);
+  // the backward reads what the forward wrote: u and new_mu are the forward's outputs
+  p->u.assign(u_out, u_out + L), p->new_mu.assign(mu_out, mu_out + L);
+  return p;
+}
+
+int b200_adam_launch_prepared(void *handle, int backward, void *stream) {
+  if (!handle) return B200_ADAM_E_ARG;
+  const PreparedPair &p = *(const PreparedPair *)handle;
+  if (!backward)
+    return b200_adam_fused_forward(p.dtype, p.L, p.g.data(), p.mu.data(), p.nu.data(), p.mu_out.data(), p.nu_out.data(),
+                                   p.u_out.data(), p.n.data(), p.count.data(), p.b1, p.b2, p.eps, p.eps_root, stream);
+  return b200_adam_fused_backward(p.dtype, p.L, p.du.data(), p.u.data(), p.new_mu.data(), p.g.data(), p.dmu_ext.data(),
+                                  p.dnu_ext.data(), p.dg.data(), p.dmu.data(), p.dnu.data(), p.n.data(), p.count.data(), p.b1,
+                                  p.b2, p.eps_root, stream);
+}
+
+int b200_adam_release_prepared(void *handle) {
+  delete (PreparedPair *)handle;
+  return 0;
 }
 
 int64_t b200_adam_bias_table_len_ex(int dtype, double b1, double b2, double eps_root) {
