@@ -100,7 +100,11 @@ def build_tools(force: bool = False, verbose: bool = True) -> list[str]:
                    "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../torchopt_b200", "-o", exe]
             if verbose:
                 print("[torchopt_b200] " + " ".join(cmd), flush=True)
-            subprocess.check_call(cmd)
+            try:
+                subprocess.check_call(cmd)
+            except subprocess.CalledProcessError as exc:   # a measurement tool must never fail the product build
+                print(f"[torchopt_b200] WARNING: tool {name} did not build ({exc}); the product is unaffected", flush=True)
+                continue
         built.append(exe)
     return built
 
