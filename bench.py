@@ -725,6 +725,42 @@ def variant_kernels(abi, torch, variant: str, n: int, iters: int = 20) -> dict:
     return res
 
 
+def leaf_sizes(abi, torch, log2_sizes=(12, 16, 20, 22, 24, 26)) -> dict:
+    """BASELINE configs[4] in brief (the full sweep is tests/perf/leaf_sweep.py -> profiles/r02_leaf_sweep.md): one fused
+    fwd+bwd pair on a single fp32 leaf of 2^k elements, issued eagerly through the C ABI (prepared launches, programmatic
+    dependent launch), best of 3 timings.  Small leaves are two launch latencies; 2^20 is L2-resident; from 2^22 on HBM."""
+    dev = torch.device("cuda")
+    peak, _ = measured_peak()
+    stream = torch.cuda.current_stream().cuda_stream
+    rows = []
+    for lg in log2_sizes:
+        n = 1 << lg
+        t = [torch.randn(n, device=dev).mul_(sc) for sc in (1e-2, 1e-2, 1.0, 1.0, 1e-3, 1e-3)]
+        t[2].abs_().mul_(1e-4)
+        o = [torch.empty(n, device=dev) for _ in range(6)]
+        g, mu, nu, du, dme, dne = ([x.data_ptr()] for x in t)
+        mu2, nu2, u, dg, dmu, dnu = ([x.data_ptr()] for x in o)
+        prep = abi.PreparedFused(abi.F32, [g, mu, nu, mu2, nu2, u], [du, u, mu2, g, dme, dne, dg, dmu, dnu], [n], [COUNT],
+                                 B1, B2, EPS, EPS_ROOT)
+        iters = 200 if lg <= 22 else 20
+        for _ in range(5):
+            prep.forward(stream), prep.backward(stream)
+        best = float("inf")
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                prep.forward(stream), prep.backward(stream)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / iters)
+        gbs = 60 * n / (best * 1e-3) / 1e9
+        rows.append({"log2n": lg, "us_per_pair": best * 1e3, "algorithmic_gbs": gbs, "frac_of_measured_peak": gbs / peak,
+                     "fits_l2": 48 * n < 100e6})
+        del prep, t, o
+    return {"workload": "single fp32 leaf, fused fwd+bwd pair (60 B/elem), eager launches through the C ABI", "rows": rows}
+
+
 def _load_example(name: str):
     import importlib.util
     spec = importlib.util.spec_from_file_location(f"b200_example_{name}", os.path.join(ROOT, "examples", f"{name}.py"))
@@ -1060,6 +1096,7 @@ def run_b200(args) -> None:
         side = [("maml_task_parallel", lambda: maml_task_parallel(tb, torch, dist, world, rank, local_rank))]  # every N
         if world == 1:
             side += [("public_api_flat", lambda: public_api_flat(tb, abi, torch)),
+                     ("leaf_sizes", lambda: leaf_sizes(abi, torch)),
                      ("roofline_f64", lambda: variant_kernels(abi, torch, "f64", 1 << 26)),
                      ("roofline_bf16", lambda: variant_kernels(abi, torch, "bf16", 1 << 28)),
                      ("resnet18_unroll5", lambda: resnet18_unroll(tb, torch)),
