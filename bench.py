@@ -1097,6 +1097,8 @@ def run_b200(args) -> None:
         if world == 1:
             side += [("public_api_flat", lambda: public_api_flat(tb, abi, torch)),
                      ("leaf_sizes", lambda: leaf_sizes(abi, torch)),
+                     # a differentiable step over a PERSISTENT state replayed from one CUDA graph (capturable=True)
+                     ("online_meta_gradient", lambda: _load_example("online_meta_gradient").measure(24, 30)),
                      ("roofline_f64", lambda: variant_kernels(abi, torch, "f64", 1 << 26)),
                      ("roofline_bf16", lambda: variant_kernels(abi, torch, "bf16", 1 << 28)),
                      ("resnet18_unroll5", lambda: resnet18_unroll(tb, torch)),
