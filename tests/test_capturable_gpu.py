@@ -347,3 +347,17 @@ def test_capturable_differentiable_abi_vs_oracle_at_any_count(c_oracle, tag):
                                                   ocol("dg"), ocol("dmu"), ocol("dnu"), None, None, ns, ptrs(cptr),
                                                   tabs[0].data_ptr(), tabs[1].data_ptr(), None, tabs[3].data_ptr(), T, b1, b2,
                                                   eps, er, -lr, 0.0, 0.0, 0, s) == -2
+
+
+def test_online_meta_gradient_example_runs_and_counts_on_the_device():
+    """examples/online_meta_gradient.py (also `extra.online_meta_gradient` of bench.py): every eager call and every graph
+    replay is one real optimizer step -- the device step count says so."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("b200_example_online", os.path.join(root, "examples", "online_meta_gradient.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rec = mod.measure(log2n=14, steps=7)
+    assert rec["device_step_count_after"] == 3 + 3 + 7      # capture warm-ups + timing warm-ups + timed replays
+    assert rec["cuda_graph_capturable_ms"] > 0 and rec["eager_default_ms"] > 0
